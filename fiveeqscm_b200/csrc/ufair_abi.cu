@@ -1,0 +1,410 @@
+// ufair_abi.cu -- extern "C" entry points of libufair.so (include/ufair.h): argument checking,
+// dispatch to the fused integrator instantiations, and the small kernels either side of it
+// (statistics reset/finalise, g_1/g_0, k_q, the reference's one-box pulse, peak microbenchmarks).
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+
+#include "../../include/ufair.h"
+#include "ufair_internal.h"
+#include "ufair_kernel.cuh"
+
+namespace ufair {
+
+static thread_local char g_err[512] = "";
+
+int set_error(int code, const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+  return code;
+}
+int cuda_error(cudaError_t e, const char* what) {
+  return set_error(UFAIR_ERR_CUDA, "%s: %s", what, cudaGetErrorString(e));
+}
+
+// ---- descriptor validation ---------------------------------------------------------------------
+static bool misaligned(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) != 0; }
+
+int validate_desc(const ufair_desc* d, size_t elem) {
+  if (!d) return set_error(UFAIR_ERR_ARG, "descriptor is NULL");
+  if (d->struct_size != sizeof(ufair_desc))
+    return set_error(UFAIR_ERR_ARG, "struct_size %u != sizeof(ufair_desc) %zu (header/binding mismatch)",
+                     d->struct_size, sizeof(ufair_desc));
+  if (d->n_gas < 1 || d->n_gas > UFAIR_MAX_GAS)
+    return set_error(UFAIR_ERR_ARG, "n_gas %d outside 1..%d", d->n_gas, UFAIR_MAX_GAS);
+  if (d->n_t < 0 || d->n_member < 0) return set_error(UFAIR_ERR_ARG, "negative n_t / n_member");
+  if (d->ld_member < d->n_member) return set_error(UFAIR_ERR_ARG, "ld_member < n_member");
+  if (d->n_member > 0 && (d->ld_member * (int64_t)elem) % 16 != 0)
+    return set_error(UFAIR_ERR_ALIGN, "ld_member %lld: rows must be a multiple of 16 bytes", (long long)d->ld_member);
+  if (d->e_mode != UFAIR_E_MEMBER && d->e_mode != UFAIR_E_SCENARIO) return set_error(UFAIR_ERR_ARG, "bad e_mode");
+  if (d->fext_mode < UFAIR_FEXT_NONE || d->fext_mode > UFAIR_FEXT_MEMBER) return set_error(UFAIR_ERR_ARG, "bad fext_mode");
+  if (d->alpha_mode < UFAIR_ALPHA_EXP || d->alpha_mode > UFAIR_ALPHA_ONE) return set_error(UFAIR_ERR_ARG, "bad alpha_mode");
+  if (d->t_mode != UFAIR_T_MID && d->t_mode != UFAIR_T_END) return set_error(UFAIR_ERR_ARG, "bad t_mode");
+  if (d->alpha_mode == UFAIR_ALPHA_NEWTON && (d->newton_iters < 0 || d->newton_iters > 8))
+    return set_error(UFAIR_ERR_ARG, "newton_iters %d outside 0..8", d->newton_iters);
+  if (d->n_scen < 1) return set_error(UFAIR_ERR_ARG, "n_scen must be >= 1");
+  if (!(d->dt > 0.0) || !(d->iirf_h > 0.0)) return set_error(UFAIR_ERR_ARG, "dt and iirf_h must be > 0");
+  if (d->n_member == 0 || d->n_t == 0) return UFAIR_OK;
+  if (!d->emissions || !d->gas_params || !d->thermal_params)
+    return set_error(UFAIR_ERR_ARG, "emissions / gas_params / thermal_params must not be NULL");
+  if (d->fext_mode != UFAIR_FEXT_NONE && !d->f_ext) return set_error(UFAIR_ERR_ARG, "fext_mode set but f_ext is NULL");
+  if ((d->out_mask & UFAIR_OUT_C) && !d->out_C) return set_error(UFAIR_ERR_ARG, "out_C requested but NULL");
+  if ((d->out_mask & UFAIR_OUT_RF) && !d->out_RF) return set_error(UFAIR_ERR_ARG, "out_RF requested but NULL");
+  if ((d->out_mask & UFAIR_OUT_T) && !d->out_T) return set_error(UFAIR_ERR_ARG, "out_T requested but NULL");
+  if ((d->out_mask & UFAIR_OUT_ALPHA) && !d->out_alpha) return set_error(UFAIR_ERR_ARG, "out_alpha requested but NULL");
+  // TMA bulk-copy sources
+  if (d->e_mode == UFAIR_E_MEMBER && misaligned(d->emissions))
+    return set_error(UFAIR_ERR_ALIGN, "emissions must be 16-byte aligned");
+  if (d->fext_mode == UFAIR_FEXT_MEMBER && misaligned(d->f_ext))
+    return set_error(UFAIR_ERR_ALIGN, "f_ext must be 16-byte aligned");
+  if (d->stats) {
+    if (d->hist_bins < 1 || d->hist_copies < 1 || !(d->hist_hi > d->hist_lo) || !d->hist_private || !d->moments_private)
+      return set_error(UFAIR_ERR_ARG, "stats requested but histogram spec/buffers incomplete");
+    if (d->hist_t0 < 0 || d->hist_rows < d->hist_t0 + d->n_t)
+      return set_error(UFAIR_ERR_ARG, "hist_rows %d < hist_t0 %d + n_t %d", d->hist_rows, d->hist_t0, d->n_t);
+  }
+  return UFAIR_OK;
+}
+
+template <typename Real> static KArgs<Real> make_args(const ufair_desc* d) {
+  KArgs<Real> a;
+  a.n_gas = d->n_gas;
+  a.n_t = d->n_t;
+  a.n_member = d->n_member;
+  a.ld = d->ld_member;
+  a.n_scen = d->n_scen;
+  a.e_mode = d->e_mode;
+  a.fext_mode = d->fext_mode;
+  a.t_mode = d->t_mode;
+  a.out_mask = d->out_mask;
+  a.stats = d->stats;
+  a.newton_iters = d->newton_iters;
+  a.clamp = (d->iirf_max > 0.0 && isfinite(d->iirf_max)) ? 1 : 0;
+  a.dt = (Real)d->dt;
+  a.h = (Real)d->iirf_h;
+  a.iirf_max = (Real)d->iirf_max;
+  a.E = (const Real*)d->emissions;
+  a.scen_idx = d->scen_idx;
+  a.e_scale = (const Real*)d->e_scale;
+  a.fext = (const Real*)d->f_ext;
+  a.gp = (const Real*)d->gas_params;
+  a.tp = (const Real*)d->thermal_params;
+  a.state_in = (const Real*)d->state_in;
+  a.oC = (Real*)d->out_C;
+  a.oRF = (Real*)d->out_RF;
+  a.oT = (Real*)d->out_T;
+  a.oA = (Real*)d->out_alpha;
+  a.state_out = (Real*)d->state_out;
+  a.hist_bins = d->hist_bins;
+  a.hist_copies = d->hist_copies;
+  a.hist_t0 = d->hist_t0;
+  a.hist_rows = d->hist_rows;
+  a.hist_lo = (Real)d->hist_lo;
+  a.hist_invw = d->stats ? (Real)((Real)d->hist_bins / ((Real)d->hist_hi - (Real)d->hist_lo)) : (Real)0;
+  a.hist = d->hist_private;
+  a.mom = d->moments_private;
+  return a;
+}
+
+template <typename Real, int NGAS> static cudaError_t dispatch_mode(const KArgs<Real>& a, int mode, cudaStream_t s) {
+  switch (mode) {
+    case UFAIR_ALPHA_EXP: return launch_integrate<Real, NGAS, UFAIR_ALPHA_EXP>(a, s);
+    case UFAIR_ALPHA_SINH: return launch_integrate<Real, NGAS, UFAIR_ALPHA_SINH>(a, s);
+    case UFAIR_ALPHA_NEWTON: return launch_integrate<Real, NGAS, UFAIR_ALPHA_NEWTON>(a, s);
+    default: return launch_integrate<Real, NGAS, UFAIR_ALPHA_ONE>(a, s);
+  }
+}
+
+template <typename Real> int run_device(const ufair_desc* d, cudaStream_t stream) {
+  int rc = validate_desc(d, sizeof(Real));
+  if (rc != UFAIR_OK) return rc;
+  if (d->n_member == 0 || d->n_t == 0) return UFAIR_OK;
+  KArgs<Real> a = make_args<Real>(d);
+  cudaError_t e;
+  switch (d->n_gas) {
+    case 1: e = dispatch_mode<Real, 1>(a, d->alpha_mode, stream); break;
+    case 2: e = dispatch_mode<Real, 2>(a, d->alpha_mode, stream); break;
+    case 3: e = dispatch_mode<Real, 3>(a, d->alpha_mode, stream); break;
+    default: e = dispatch_mode<Real, 4>(a, d->alpha_mode, stream); break;
+  }
+  if (e != cudaSuccess) return cuda_error(e, "ufair_integrate_kernel launch");
+  return UFAIR_OK;
+}
+template int run_device<double>(const ufair_desc*, cudaStream_t);
+template int run_device<float>(const ufair_desc*, cudaStream_t);
+
+// ---- statistics buffers -------------------------------------------------------------------------
+__global__ void stats_reset_kernel(unsigned int* hist, size_t n_hist, double* mom, size_t n_rows) {
+  const size_t i0 = (size_t)blockIdx.x * blockDim.x + threadIdx.x, stride = (size_t)gridDim.x * blockDim.x;
+  for (size_t i = i0; i < n_hist; i += stride) hist[i] = 0u;
+  for (size_t i = i0; i < n_rows; i += stride) {
+    double* r = mom + i * UFAIR_MOM_COUNT;
+    r[UFAIR_MOM_SUM] = 0.0;
+    r[UFAIR_MOM_SUMSQ] = 0.0;
+    reinterpret_cast<unsigned long long*>(r)[UFAIR_MOM_MIN] = 0xffffffffffffffffull;
+    reinterpret_cast<unsigned long long*>(r)[UFAIR_MOM_MAX] = 0ull;
+  }
+}
+
+__global__ void stats_finalize_kernel(const unsigned int* hp, const double* mp, int copies, int rows, int bins,
+                                      unsigned long long* hist, double* mom) {
+  const size_t n = (size_t)rows * bins;
+  const size_t i0 = (size_t)blockIdx.x * blockDim.x + threadIdx.x, stride = (size_t)gridDim.x * blockDim.x;
+  for (size_t i = i0; i < n; i += stride) {
+    unsigned long long s = 0;
+    for (int c = 0; c < copies; ++c) s += hp[(size_t)c * n + i];
+    hist[i] = s;
+  }
+  for (size_t r = i0; r < (size_t)rows; r += stride) {
+    double sm = 0.0, ss = 0.0;
+    unsigned long long mn = 0xffffffffffffffffull, mx = 0ull;
+    for (int c = 0; c < copies; ++c) {  // fixed order: deterministic given the private copies
+      const double* p = mp + ((size_t)c * rows + r) * UFAIR_MOM_COUNT;
+      sm += p[UFAIR_MOM_SUM];
+      ss += p[UFAIR_MOM_SUMSQ];
+      const unsigned long long a = reinterpret_cast<const unsigned long long*>(p)[UFAIR_MOM_MIN];
+      const unsigned long long b = reinterpret_cast<const unsigned long long*>(p)[UFAIR_MOM_MAX];
+      mn = a < mn ? a : mn;
+      mx = b > mx ? b : mx;
+    }
+    double* o = mom + r * UFAIR_MOM_COUNT;
+    o[UFAIR_MOM_SUM] = sm;
+    o[UFAIR_MOM_SUMSQ] = ss;
+    o[UFAIR_MOM_MIN] = dec_ordered(mn);
+    o[UFAIR_MOM_MAX] = dec_ordered(mx);
+  }
+}
+
+static int check_stats_desc(const ufair_desc* d) {
+  if (!d || d->struct_size != sizeof(ufair_desc)) return set_error(UFAIR_ERR_ARG, "bad descriptor");
+  if (d->hist_bins < 1 || d->hist_copies < 1 || d->hist_rows < 1 || !d->hist_private || !d->moments_private)
+    return set_error(UFAIR_ERR_ARG, "histogram spec/buffers incomplete");
+  return UFAIR_OK;
+}
+
+// ---- parameter preparation ------------------------------------------------------------------------
+__global__ void g1g0_kernel(const double* a, const double* tau, long long n, long long ld, double h, int mode,
+                            double* g1o, double* g0o) {
+  const long long m = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (m >= n) return;
+  double g1 = 0.0, s = 0.0;
+  for (int i = 0; i < 4; ++i) {
+    const double ai = a[i * ld + m], ti = tau[i * ld + m];
+    const double z = h / ti, ez = exp(-z);
+    g1 += ai * ti * (1.0 - (1.0 + z) * ez);
+    s += ai * ti * (1.0 - ez);
+  }
+  s /= g1;
+  g1o[m] = g1;
+  g0o[m] = (mode == UFAIR_ALPHA_SINH) ? 1.0 / sinh(s) : exp(-s);
+}
+
+__global__ void kq_kernel(const double* tcr, const double* ecs, const double* d1, const double* d2, double f2x,
+                          long long n, double* q1, double* q2) {
+  const long long m = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (m >= n) return;
+  const double k1 = 1.0 - (d1[m] / 70.0) * (1.0 - exp(-70.0 / d1[m]));
+  const double k2 = 1.0 - (d2[m] / 70.0) * (1.0 - exp(-70.0 / d2[m]));
+  const double den = f2x * (k1 - k2);
+  q1[m] = (tcr[m] - ecs[m] * k2) / den;
+  q2[m] = (ecs[m] * k1 - tcr[m]) / den;
+}
+
+// reference U_FaIR/concentrations.py:5 -- emissions[0] * np.exp(-time), on broadcast operands.
+// __dmul_rn: the product is rounded on its own, exactly like numpy's separate multiply.
+__global__ void hfc_pulse_kernel(const double* e0, const double* time, double* out, long long n) {
+  const long long i0 = (long long)blockIdx.x * blockDim.x + threadIdx.x, stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = i0; i < n; i += stride) out[i] = __dmul_rn(e0[i], exp(-time[i]));
+}
+
+// ---- device-math probe (tests/test_gpu_math.py) ---------------------------------------------------
+template <typename Real> __global__ void math_probe_kernel(int op, const Real* x, Real* y, long long n) {
+  using M = Math<Real>;
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const Real v = x[i];
+  Real r;
+  switch (op) {
+    case 0: r = M::decay(v); break;
+    case 1: r = M::exp_(v); break;
+    case 2: r = M::rcp(v); break;
+    case 3: r = M::sqrt_(v); break;
+    case 4: r = M::log_(v); break;
+    default: r = M::sinh_pair(v); break;
+  }
+  y[i] = r;
+}
+
+// ---- peak microbenchmarks ---------------------------------------------------------------------------
+template <typename T> __global__ void __launch_bounds__(256) peak_fma_kernel(int iters, T* sink) {
+  T a[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) a[j] = T(1) + T(threadIdx.x + j) * T(1e-6);
+  const T b = T(0.999999), c = T(1e-7);
+  for (int i = 0; i < iters; ++i) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) a[j] = a[j] * b + c;  // contracted to one FMA per line
+  }
+  T s = 0;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) s += a[j];
+  if (s == T(-12345)) sink[0] = s;  // never true; keeps the chains alive
+}
+__global__ void __launch_bounds__(256) peak_mufu_kernel(int iters, float* sink) {
+  float a[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) a[j] = 0.001f * (threadIdx.x + j);
+  for (int i = 0; i < iters; ++i) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) asm volatile("ex2.approx.ftz.f32 %0, %0;" : "+f"(a[j]));
+  }
+  float s = 0;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) s += a[j];
+  if (s == -12345.f) sink[0] = s;
+}
+
+template <typename Launch> static int time_kernel(Launch&& launch, cudaStream_t s, double* ms) {
+  cudaEvent_t e0, e1;
+  cudaError_t e;
+  if ((e = cudaEventCreate(&e0)) != cudaSuccess) return cuda_error(e, "cudaEventCreate");
+  if ((e = cudaEventCreate(&e1)) != cudaSuccess) return cuda_error(e, "cudaEventCreate");
+  launch();  // warm-up
+  cudaEventRecord(e0, s);
+  launch();
+  cudaEventRecord(e1, s);
+  e = cudaEventSynchronize(e1);
+  float t = 0.f;
+  if (e == cudaSuccess) e = cudaEventElapsedTime(&t, e0, e1);
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  if (e != cudaSuccess) return cuda_error(e, "peak kernel");
+  *ms = t;
+  return UFAIR_OK;
+}
+
+static int peak_grid() {
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  return sms * 8;
+}
+
+}  // namespace ufair
+
+using namespace ufair;
+
+extern "C" {
+
+int ufair_abi_version(void) { return UFAIR_ABI_VERSION; }
+const char* ufair_last_error(void) { return g_err; }
+int64_t ufair_block_members(void) { return kBlock; }
+
+int ufair_run_f64(const ufair_desc* d, void* stream) { return run_device<double>(d, (cudaStream_t)stream); }
+int ufair_run_f32(const ufair_desc* d, void* stream) { return run_device<float>(d, (cudaStream_t)stream); }
+
+int ufair_stats_reset(const ufair_desc* d, void* stream) {
+  int rc = check_stats_desc(d);
+  if (rc != UFAIR_OK) return rc;
+  const size_t rows = (size_t)d->hist_copies * d->hist_rows;
+  stats_reset_kernel<<<592, 256, 0, (cudaStream_t)stream>>>(d->hist_private, rows * d->hist_bins, d->moments_private, rows);
+  cudaError_t e = cudaGetLastError();
+  return e == cudaSuccess ? UFAIR_OK : cuda_error(e, "stats_reset_kernel");
+}
+
+int ufair_stats_finalize(const ufair_desc* d, uint64_t* hist, double* moments, void* stream) {
+  int rc = check_stats_desc(d);
+  if (rc != UFAIR_OK) return rc;
+  if (!hist || !moments) return set_error(UFAIR_ERR_ARG, "hist / moments output is NULL");
+  stats_finalize_kernel<<<592, 256, 0, (cudaStream_t)stream>>>(d->hist_private, d->moments_private, d->hist_copies,
+                                                               d->hist_rows, d->hist_bins,
+                                                               (unsigned long long*)hist, moments);
+  cudaError_t e = cudaGetLastError();
+  return e == cudaSuccess ? UFAIR_OK : cuda_error(e, "stats_finalize_kernel");
+}
+
+int ufair_g1g0_f64(const double* a, const double* tau, int64_t n, int64_t ld, double h, int32_t mode, double* g1,
+                   double* g0, void* stream) {
+  if (n < 0 || ld < n || !(h > 0.0)) return set_error(UFAIR_ERR_ARG, "bad n / ld / h");
+  if (n == 0) return UFAIR_OK;
+  if (!a || !tau || !g1 || !g0) return set_error(UFAIR_ERR_ARG, "NULL pointer");
+  g1g0_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(a, tau, n, ld, h, mode, g1, g0);
+  cudaError_t e = cudaGetLastError();
+  return e == cudaSuccess ? UFAIR_OK : cuda_error(e, "g1g0_kernel");
+}
+
+int ufair_kq_f64(const double* tcr, const double* ecs, const double* d1, const double* d2, double f2x, int64_t n,
+                 double* q1, double* q2, void* stream) {
+  if (n < 0) return set_error(UFAIR_ERR_ARG, "bad n");
+  if (n == 0) return UFAIR_OK;
+  if (!tcr || !ecs || !d1 || !d2 || !q1 || !q2) return set_error(UFAIR_ERR_ARG, "NULL pointer");
+  kq_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(tcr, ecs, d1, d2, f2x, n, q1, q2);
+  cudaError_t e = cudaGetLastError();
+  return e == cudaSuccess ? UFAIR_OK : cuda_error(e, "kq_kernel");
+}
+
+int ufair_hfc_pulse_f64(const double* e0, const double* time, double* out, int64_t n, void* stream) {
+  if (n < 0) return set_error(UFAIR_ERR_ARG, "bad n");
+  if (n == 0) return UFAIR_OK;
+  if (!e0 || !time || !out) return set_error(UFAIR_ERR_ARG, "NULL pointer");
+  const unsigned grid = (unsigned)((n + 255) / 256 < 148 * 16 ? (n + 255) / 256 : 148 * 16);
+  hfc_pulse_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(e0, time, out, n);
+  cudaError_t e = cudaGetLastError();
+  return e == cudaSuccess ? UFAIR_OK : cuda_error(e, "hfc_pulse_kernel");
+}
+
+int ufair_math_probe_f64(int op, const double* x, double* y, int64_t n, void* stream) {
+  if (n <= 0) return UFAIR_OK;
+  math_probe_kernel<double><<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(op, x, y, n);
+  cudaError_t e = cudaGetLastError();
+  return e == cudaSuccess ? UFAIR_OK : cuda_error(e, "math_probe_kernel");
+}
+int ufair_math_probe_f32(int op, const float* x, float* y, int64_t n, void* stream) {
+  if (n <= 0) return UFAIR_OK;
+  math_probe_kernel<float><<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(op, x, y, n);
+  cudaError_t e = cudaGetLastError();
+  return e == cudaSuccess ? UFAIR_OK : cuda_error(e, "math_probe_kernel");
+}
+
+int ufair_peak_fp64(int iters, double* ms, double* flops, void* stream) {
+  if (iters < 1 || !ms || !flops) return set_error(UFAIR_ERR_ARG, "bad args");
+  double* sink = nullptr;
+  cudaError_t e = cudaMalloc(&sink, sizeof(double));
+  if (e != cudaSuccess) return cuda_error(e, "cudaMalloc");
+  const int grid = peak_grid();
+  int rc = time_kernel([&] { peak_fma_kernel<double><<<grid, 256, 0, (cudaStream_t)stream>>>(iters, sink); },
+                       (cudaStream_t)stream, ms);
+  cudaFree(sink);
+  *flops = 2.0 * 8.0 * (double)iters * 256.0 * grid;
+  return rc;
+}
+int ufair_peak_fp32(int iters, double* ms, double* flops, void* stream) {
+  if (iters < 1 || !ms || !flops) return set_error(UFAIR_ERR_ARG, "bad args");
+  float* sink = nullptr;
+  cudaError_t e = cudaMalloc(&sink, sizeof(float));
+  if (e != cudaSuccess) return cuda_error(e, "cudaMalloc");
+  const int grid = peak_grid();
+  int rc = time_kernel([&] { peak_fma_kernel<float><<<grid, 256, 0, (cudaStream_t)stream>>>(iters, sink); },
+                       (cudaStream_t)stream, ms);
+  cudaFree(sink);
+  *flops = 2.0 * 8.0 * (double)iters * 256.0 * grid;
+  return rc;
+}
+int ufair_peak_mufu(int iters, double* ms, double* ops, void* stream) {
+  if (iters < 1 || !ms || !ops) return set_error(UFAIR_ERR_ARG, "bad args");
+  float* sink = nullptr;
+  cudaError_t e = cudaMalloc(&sink, sizeof(float));
+  if (e != cudaSuccess) return cuda_error(e, "cudaMalloc");
+  const int grid = peak_grid();
+  int rc = time_kernel([&] { peak_mufu_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(iters, sink); },
+                       (cudaStream_t)stream, ms);
+  cudaFree(sink);
+  *ops = 8.0 * (double)iters * 256.0 * grid;
+  return rc;
+}
+
+}  // extern "C"

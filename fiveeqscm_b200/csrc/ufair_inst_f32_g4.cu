@@ -1,0 +1,8 @@
+// explicit instantiations of the fused integrator: float, 4 gas(es), all alpha modes
+#include "ufair_kernel.cuh"
+namespace ufair {
+UFAIR_DEFINE_LAUNCH(float, 4, UFAIR_ALPHA_EXP)
+UFAIR_DEFINE_LAUNCH(float, 4, UFAIR_ALPHA_SINH)
+UFAIR_DEFINE_LAUNCH(float, 4, UFAIR_ALPHA_NEWTON)
+UFAIR_DEFINE_LAUNCH(float, 4, UFAIR_ALPHA_ONE)
+}  // namespace ufair

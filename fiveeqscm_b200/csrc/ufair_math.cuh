@@ -1,0 +1,210 @@
+// ufair_math.cuh -- device math for the Universal-FaIR integrator (sm_100a).
+//
+// The FP64 pipe is the binding unit of the FP64 hot loop (15 exp + 3 log + 3 sqrt + 3 rcp per
+// member-step), so the transcendentals are hand-rolled here with exactly the properties the
+// model needs, instead of calling the general-purpose CUDA libm versions:
+//   decay(x) = 1 - exp(-x)  accurate for tiny x (no cancellation; the oracle uses -expm1(-x)),
+//   exp_scaled(u)           for alpha = exp(u),
+//   rcp / sqrt              MUFU seed + Newton, no special-case slow paths (operands are
+//                           positive normal numbers on this path; edge cases handled explicitly),
+//   log                     atanh-series with a reciprocal instead of a division.
+// Polynomial coefficients come from tools/gen_poly.py (near-minimax, error re-measured with the
+// rounded coefficients): expm1 Q deg 9 max rel err 4.1e-17; log L deg 6 4.6e-18 (f64);
+// expm1 Q deg 4 2.3e-8; log via MUFU.LG2 (f32).
+// Measured accuracy vs mpmath on the GPU: tests/test_gpu_math.py.
+#pragma once
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdint.h>
+
+namespace ufair {
+
+template <typename Real> struct Math;
+
+// ------------------------------------------------------------------------------------ FP64
+template <> struct Math<double> {
+  using real = double;
+  static constexpr double kLog2e = 0x1.71547652b82fep+0;
+  static constexpr double kLn2Hi = 0x1.62e42fefa39efp-1;
+  static constexpr double kLn2Lo = 0x1.abc9e3b39803fp-56;
+  static constexpr double kMagic = 0x1.8p52;  // 2^52 + 2^51: rint + integer in the low word
+
+  // expm1(r) for |r| <= ln2/2:  r + r^2 Q(r)
+  static __device__ __forceinline__ double expm1_reduced(double r) {
+    double q = 0x1.af389ecfc4b9cp-26;
+    q = fma(q, r, 0x1.28917c89a43a7p-22);
+    q = fma(q, r, 0x1.71de0db2f6b19p-19);
+    q = fma(q, r, 0x1.a019b9149a41cp-16);
+    q = fma(q, r, 0x1.a01a01a7c2efep-13);
+    q = fma(q, r, 0x1.6c16c17889ef1p-10);
+    q = fma(q, r, 0x1.11111111109b5p-7);
+    q = fma(q, r, 0x1.5555555553d68p-5);
+    q = fma(q, r, 0x1.5555555555556p-3);
+    q = fma(q, r, 0x1.0000000000001p-1);
+    return fma(r * r, q, r);
+  }
+
+  // y = n ln2 + r with n = rint(y log2 e); returns r, n through `n`
+  static __device__ __forceinline__ double reduce(double y, int& n) {
+    double t = fma(y, kLog2e, kMagic);
+    n = __double2loint(t);
+    double nd = t - kMagic;
+    double r = fma(nd, -kLn2Hi, y);
+    return fma(nd, -kLn2Lo, r);
+  }
+
+  // m = 1 - exp(-x).  x >= 0 expected (any finite x works); NaN propagates.
+  static __device__ __forceinline__ double decay(double x) {
+    double y = -x;
+    y = (y < -45.0) ? -45.0 : y;  // 1 - e^-45 rounds to 1; keeps 2^n normal. NaN falls through.
+    int n;
+    double r = reduce(y, n);
+    double p = expm1_reduced(r);
+    n = max(min(n, 1000), -1000);
+    double s = __hiloint2double((1023 + n) << 20, 0);  // 2^n (exact)
+    return fma(-s, p, 1.0 - s);                         // 1 - s(1 + p); 1 - s is exact for n <= 0
+  }
+
+  // exp(u); saturates (instead of overflowing) outside 2^+-1000; NaN/inf -> NaN.
+  static __device__ __forceinline__ double exp_(double u) {
+    int n;
+    double r = reduce(u, n);
+    double v = 1.0 + expm1_reduced(r);
+    n = max(min(n, 1000), -1000);
+    return __hiloint2double(__double2hiint(v) + (n << 20), __double2loint(v));
+  }
+
+  // 1/a for positive normal a: MUFU.RCP64H seed + 2 Newton steps (4 DFMA), ~1 ulp.
+  static __device__ __forceinline__ double rcp(double a) {
+    double y;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(a));
+    double e = fma(-a, y, 1.0);
+    y = fma(y, e, y);
+    e = fma(-a, y, 1.0);
+    return fma(y, e, y);
+  }
+
+  // sqrt(a) for a >= 0: MUFU.RSQ64H seed + 2 coupled Newton steps; sqrt(0) = 0; a < 0 -> NaN.
+  static __device__ __forceinline__ double sqrt_(double a) {
+    double y;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(a));
+    double g = a * y, h = 0.5 * y;
+    double r = fma(-g, h, 0.5);
+    g = fma(g, r, g);
+    h = fma(h, r, h);
+    r = fma(-g, h, 0.5);
+    g = fma(g, r, g);
+    return (a == 0.0) ? 0.0 : g;
+  }
+
+  // log(y).  Positive normal y on the fast path; everything else takes the (never hot) libm call.
+  static __device__ __forceinline__ double log_(double y) {
+    int hi = __double2hiint(y), lo = __double2loint(y);
+    if (__builtin_expect((unsigned)(hi - 0x00100000) >= 0x7fe00000u, 0)) return log(y);
+    int e = (hi >> 20) - 1023;
+    int mh = (hi & 0x000fffff) | 0x3ff00000;  // mantissa in [1,2)
+    if (mh > 0x3ff6a09e) {                     // > sqrt(2): halve
+      mh -= 0x00100000;
+      e += 1;
+    }
+    double m = __hiloint2double(mh, lo);
+    double f = m - 1.0;
+    double s = f * rcp(m + 1.0);
+    double w = s * s;
+    double L = 0x1.2b584aae78a57p-3;
+    L = fma(L, w, 0x1.39fe606542ddep-3);
+    L = fma(L, w, 0x1.7462b4ab2ef6bp-3);
+    L = fma(L, w, 0x1.c71c62e5800a1p-3);
+    L = fma(L, w, 0x1.2492492df148dp-2);
+    L = fma(L, w, 0x1.99999999952e2p-2);
+    L = fma(L, w, 0x1.5555555555558p-1);
+    double ed = __hiloint2double(0x43300000, e ^ 0x80000000) - 0x1.0000080000000p52;  // (double)e
+    double t = fma(s * w, L, ed * kLn2Lo);
+    t = fma(2.0, s, t);
+    return fma(ed, kLn2Hi, t);
+  }
+
+  static __device__ __forceinline__ double fmin_(double a, double b) { return fmin(a, b); }
+  static __device__ __forceinline__ double fmax_(double a, double b) { return fmax(a, b); }
+  static __device__ __forceinline__ double floor_(double a) { return floor(a); }
+  static __device__ __forceinline__ double exp_ref(double a) { return exp(a); }
+  // histogram coordinate: subtract, then multiply, each rounded (no FMA contraction) so the
+  // binning is reproducible on the host
+  static __device__ __forceinline__ double bin_x(double T, double lo, double invw) {
+    return __dmul_rn(__dsub_rn(T, lo), invw);
+  }
+  static __device__ __forceinline__ double sinh_pair(double v) {  // sinh via exp and 1/exp
+    double e = exp_(v);
+    return 0.5 * (e - rcp(e));
+  }
+};
+
+// ------------------------------------------------------------------------------------ FP32
+template <> struct Math<float> {
+  using real = float;
+  static constexpr float kLog2e = 1.4426950408889634f;
+  static constexpr float kLn2Hi = 0.693145751953125f;       // 12 trailing zero bits
+  static constexpr float kLn2Lo = 1.42860682030941723e-6f;
+  static constexpr float kMagic = 12582912.0f;  // 1.5 * 2^23
+
+  static __device__ __forceinline__ float expm1_reduced(float r) {
+    float q = 1.392617589e-03f;
+    q = fmaf(q, r, 8.363173343e-03f);
+    q = fmaf(q, r, 4.166655615e-02f);
+    q = fmaf(q, r, 1.666657776e-01f);
+    q = fmaf(q, r, 5.000000000e-01f);
+    return fmaf(r * r, q, r);
+  }
+  static __device__ __forceinline__ float reduce(float y, int& n) {
+    float t = fmaf(y, kLog2e, kMagic);
+    n = __float_as_int(t) - 0x4b400000;
+    float nd = t - kMagic;
+    float r = fmaf(nd, -kLn2Hi, y);
+    return fmaf(nd, -kLn2Lo, r);
+  }
+  static __device__ __forceinline__ float decay(float x) {
+    float y = -x;
+    y = (y < -20.0f) ? -20.0f : y;
+    int n;
+    float r = reduce(y, n);
+    float p = expm1_reduced(r);
+    n = max(min(n, 120), -120);
+    float s = __int_as_float((127 + n) << 23);
+    return fmaf(-s, p, 1.0f - s);
+  }
+  static __device__ __forceinline__ float exp_(float u) {
+    int n;
+    float r = reduce(u, n);
+    float v = 1.0f + expm1_reduced(r);
+    n = max(min(n, 120), -120);
+    return __int_as_float(__float_as_int(v) + (n << 23));
+  }
+  static __device__ __forceinline__ float rcp(float a) {
+    float y;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(a));
+    return y;
+  }
+  static __device__ __forceinline__ float sqrt_(float a) {
+    float y;
+    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(a));
+    return y;
+  }
+  static __device__ __forceinline__ float log_(float y) {
+    float l;
+    asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(l) : "f"(y));
+    return l * 0.6931471805599453f;
+  }
+  static __device__ __forceinline__ float fmin_(float a, float b) { return fminf(a, b); }
+  static __device__ __forceinline__ float fmax_(float a, float b) { return fmaxf(a, b); }
+  static __device__ __forceinline__ float floor_(float a) { return floorf(a); }
+  static __device__ __forceinline__ float exp_ref(float a) { return expf(a); }
+  static __device__ __forceinline__ float bin_x(float T, float lo, float invw) {
+    return __fmul_rn(__fsub_rn(T, lo), invw);
+  }
+  static __device__ __forceinline__ float sinh_pair(float v) {
+    float e = exp_(v);
+    return 0.5f * (e - rcp(e));
+  }
+};
+
+}  // namespace ufair

@@ -155,8 +155,8 @@ typedef struct ufair_desc {
 int ufair_abi_version(void);
 const char* ufair_last_error(void);
 
-/* Largest members-per-call chunk that keeps every array index below 2^31 rows etc.
- * (informational; the run functions accept any n_member that fits memory). */
+/* Members per CTA of the integrator (informational: chunk sizes that are a multiple of it
+ * waste no lanes; the run functions accept any n_member). */
 int64_t ufair_block_members(void);
 
 /* ---- the hot path: oxfair (driver loop) with step_conc/alpha_val/step_forc/step_temp fused ---- */
@@ -190,6 +190,11 @@ int ufair_workspace_create(int device, int64_t chunk_members, ufair_workspace** 
 int ufair_workspace_destroy(ufair_workspace* ws);
 int ufair_run_host_f64(ufair_workspace* ws, const ufair_desc* d, uint64_t* hist, double* moments);
 int ufair_run_host_f32(ufair_workspace* ws, const ufair_desc* d, uint64_t* hist, double* moments);
+
+/* ---- device-math probe (test support): y[i] = op(x[i]) with the kernel's own math routines.
+ * op: 0 decay(x)=1-exp(-x), 1 exp, 2 rcp, 3 sqrt, 4 log, 5 sinh. */
+int ufair_math_probe_f64(int op, const double* x, double* y, int64_t n, void* stream);
+int ufair_math_probe_f32(int op, const float* x, float* y, int64_t n, void* stream);
 
 /* ---- measured-peak microbenchmarks used by bench.py for the roofline denominators ---- */
 /* Runs `iters` dependent-chain DFMA (or FFMA / MUFU.EX2) per thread over a full grid and

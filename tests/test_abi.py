@@ -1,0 +1,89 @@
+"""CPU checks of the drop-in boundary: the C-ABI library exists, loads, and exports every symbol
+include/ufair.h declares (no compute calls -- those need a GPU)."""
+import ctypes
+import os
+import re
+
+import pytest
+
+from fiveeqscm_b200 import _abi
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+HEADER = os.path.join(ROOT, "include", "ufair.h")
+
+
+def _declared_functions():
+    src = open(HEADER).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(ufair_[a-z0-9_]+)\s*\(", src)))
+
+
+@pytest.fixture(scope="module")
+def built():
+    if not os.path.exists(_abi.lib_path()):
+        import __graft_entry__ as g
+        g.build()
+    return _abi.lib_path()
+
+
+def test_header_declares_the_expected_entry_points():
+    names = _declared_functions()
+    for must in ("ufair_run_f64", "ufair_run_f32", "ufair_hfc_pulse_f64", "ufair_stats_finalize",
+                 "ufair_g1g0_f64", "ufair_kq_f64", "ufair_run_host_f64", "ufair_last_error"):
+        assert must in names
+
+
+def test_library_exports_every_declared_symbol(built):
+    L = ctypes.CDLL(built)
+    for name in _declared_functions():
+        assert hasattr(L, name), f"{name} declared in include/ufair.h but not exported by libufair.so"
+
+
+def test_binding_covers_every_declared_symbol():
+    assert sorted(_abi.SIGNATURES) == _declared_functions()
+
+
+def test_abi_version_and_struct_size(built):
+    L = _abi.lib()
+    assert L.ufair_abi_version() == _abi.ABI_VERSION
+    assert L.ufair_block_members() == 128
+    # a descriptor with the wrong struct_size is rejected before anything touches the device
+    d = _abi.UfairDesc(n_gas=1, n_t=1, n_member=1, ld_member=2)
+    d.struct_size = 8
+    assert L.ufair_run_f64(ctypes.byref(d), None) == _abi.ERR_ARG
+    assert b"struct_size" in L.ufair_last_error()
+
+
+def test_argument_errors_are_reported_not_fatal(built):
+    L = _abi.lib()
+    d = _abi.UfairDesc(n_gas=9, n_t=1, n_member=1, ld_member=2)
+    assert L.ufair_run_f64(ctypes.byref(d), None) == _abi.ERR_ARG
+    d = _abi.UfairDesc(n_gas=1, n_t=4, n_member=3, ld_member=3)   # 24-byte rows: not 16-byte aligned
+    assert L.ufair_run_f64(ctypes.byref(d), None) == _abi.ERR_ALIGN
+    d = _abi.UfairDesc(n_gas=1, n_t=4, n_member=4, ld_member=4)   # NULL inputs
+    assert L.ufair_run_f64(ctypes.byref(d), None) == _abi.ERR_ARG
+    d = _abi.UfairDesc(n_gas=1, n_t=4, n_member=4, ld_member=4, alpha_mode=7)
+    assert L.ufair_run_f64(ctypes.byref(d), None) == _abi.ERR_ARG
+    with pytest.raises(_abi.UfairError):
+        _abi.check(L.ufair_run_f32(ctypes.byref(d), None))
+
+
+def test_oracle_struct_layout_matches_c(built):
+    # the C oracle checks struct_size against its own sizeof(ufair_desc): same header, same layout
+    from oracle import c_oracle
+    d = _abi.UfairDesc(n_gas=1, n_t=0, n_member=0, ld_member=0)
+    assert c_oracle.lib().ufo_run_f64(ctypes.byref(d), 1) >= 1
+
+
+def test_product_never_imports_the_oracle():
+    pkg = os.path.join(ROOT, "fiveeqscm_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                text = open(os.path.join(dirpath, f)).read()
+                assert "oracle" not in text.replace("the oracle", "").replace("float64 oracle", "").lower() or \
+                    "import oracle" not in text and "from oracle" not in text, f
+    for f in os.listdir(os.path.join(ROOT, "U_FaIR")):
+        if f.endswith(".py"):
+            text = open(os.path.join(ROOT, "U_FaIR", f)).read()
+            assert "import oracle" not in text and "from oracle" not in text

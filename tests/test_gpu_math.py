@@ -1,0 +1,84 @@
+"""Accuracy of the hand-rolled device math (csrc/ufair_math.cuh) against numpy/mpmath, in ulps."""
+import numpy as np
+import pytest
+
+from fiveeqscm_b200 import _abi
+from tests.util import to_dev, to_np
+
+pytestmark = pytest.mark.gpu
+
+OPS = {"decay": 0, "exp": 1, "rcp": 2, "sqrt": 3, "log": 4, "sinh": 5}
+
+
+def _probe(op, x):
+    import torch
+    L = _abi.lib()
+    xd = to_dev(x)
+    yd = torch.empty_like(xd)
+    fn = L.ufair_math_probe_f64 if x.dtype == np.float64 else L.ufair_math_probe_f32
+    _abi.check(fn(OPS[op], xd.data_ptr(), yd.data_ptr(), x.size, None))
+    torch.cuda.synchronize()
+    return to_np(yd)
+
+
+def _ulps(got, ref):
+    ref = np.asarray(ref, dtype=np.longdouble)
+    sp = np.spacing(np.abs(ref.astype(got.dtype)))
+    return np.max(np.abs(got.astype(np.longdouble) - ref) / sp)
+
+
+def _ld(x):
+    return x.astype(np.longdouble)
+
+
+@pytest.fixture(scope="module")
+def rng():
+    return np.random.default_rng(99)
+
+
+def test_decay_f64(rng):
+    x = np.concatenate([10.0 ** rng.uniform(-12, 2, 200_000), rng.uniform(0, 3, 200_000), [0.0, 1e-300, 44.9, 45.1, 800.0]])
+    got = _probe("decay", x)
+    ref = -np.expm1(-_ld(x))
+    assert _ulps(got, ref) <= 2.0
+    assert got[-5] == 0.0 and got[-1] == 1.0
+
+
+def test_exp_f64(rng):
+    x = np.concatenate([rng.uniform(-30, 30, 300_000), rng.uniform(-1e-3, 1e-3, 1000), [0.0, -700.0, 700.0]])
+    assert _ulps(_probe("exp", x), np.exp(_ld(x))) <= 2.0
+
+
+def test_rcp_sqrt_f64(rng):
+    x = 10.0 ** rng.uniform(-30, 30, 300_000)
+    assert _ulps(_probe("rcp", x), 1.0 / _ld(x)) <= 1.5
+    assert _ulps(_probe("sqrt", x), np.sqrt(_ld(x))) <= 1.5
+    z = _probe("sqrt", np.array([0.0, 4.0, -1.0]))
+    assert z[0] == 0.0 and z[1] == 2.0 and np.isnan(z[2])
+
+
+def test_log_f64(rng):
+    x = np.concatenate([10.0 ** rng.uniform(-5, 5, 200_000), 1.0 + rng.uniform(-1e-3, 1e-3, 100_000),
+                        rng.uniform(0.5, 2.0, 100_000)])
+    assert _ulps(_probe("log", x), np.log(_ld(x))) <= 2.0
+    z = _probe("log", np.array([1.0, 0.0, -1.0, np.inf, 5e-324]))
+    assert z[0] == 0.0 and z[1] == -np.inf and np.isnan(z[2]) and z[3] == np.inf
+    assert abs(z[4] - np.log(5e-324)) < 1e-10
+
+
+def test_sinh_f64(rng):
+    x = rng.uniform(0.5, 12.0, 100_000)
+    assert _ulps(_probe("sinh", x), np.sinh(_ld(x))) <= 8.0
+
+
+def test_f32_math(rng):
+    x = np.concatenate([10.0 ** rng.uniform(-8, 1, 100_000), rng.uniform(0, 3, 100_000)]).astype(np.float32)
+    got = _probe("decay", x)
+    ref = -np.expm1(-x.astype(np.float64))
+    assert np.max(np.abs(got - ref) / np.maximum(np.abs(ref), 1e-30)) < 4e-7
+    u = rng.uniform(-20, 20, 100_000).astype(np.float32)
+    assert np.max(np.abs(_probe("exp", u) / np.exp(u.astype(np.float64)) - 1)) < 4e-7
+    p = (10.0 ** rng.uniform(-3, 4, 100_000)).astype(np.float32)
+    assert np.max(np.abs(_probe("sqrt", p) / np.sqrt(p.astype(np.float64)) - 1)) < 4e-7
+    assert np.max(np.abs(_probe("rcp", p) * p.astype(np.float64) - 1)) < 4e-7
+    assert np.max(np.abs(_probe("log", p) - np.log(p.astype(np.float64)))) < 2e-6

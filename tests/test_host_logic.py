@@ -1,0 +1,138 @@
+"""CPU tests of the host-side logic: sharding plan, statistics post-processing, the
+world_size-2 reduction over gloo, argument validation and the loud no-fallback behaviour."""
+import os
+import subprocess
+import sys
+import textwrap
+
+import numpy as np
+import pytest
+
+from fiveeqscm_b200 import concentrations as conc
+from fiveeqscm_b200 import dist as D
+from fiveeqscm_b200 import params as P
+from fiveeqscm_b200 import stats as S
+from oracle import c_oracle as co
+from oracle import ufair_oracle as o
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_shard_bounds_cover_and_align():
+    for n in (0, 1, 127, 128, 129, 10_000, 10_000_000):
+        for w in (1, 2, 4, 8):
+            edges = [D.shard_bounds(n, w, r) for r in range(w)]
+            assert edges[0][0] == 0 and edges[-1][1] == n
+            for (lo, hi), (lo2, _) in zip(edges, edges[1:]):
+                assert hi == lo2 and lo <= hi
+            for lo, hi in edges[:-1]:
+                assert lo % 128 == 0 and hi % 128 == 0
+    lo, hi = D.shard_bounds(10_000_000, 8, 3)
+    assert abs((hi - lo) - 1_250_000) <= 128
+    with pytest.raises(ValueError):
+        D.shard_bounds(10, 2, 2)
+
+
+def test_percentiles_and_moments_postprocessing():
+    rng = np.random.default_rng(0)
+    T = rng.normal(2.0, 0.7, size=(5, 50_000))
+    hist, mom = o.temperature_stats(T, -5.0, 25.0, 1024)
+    pct = S.percentiles(hist, -5.0, 25.0, [5, 50, 95])
+    np.testing.assert_allclose(pct, o.percentiles_from_hist(hist, -5.0, 25.0, [5, 50, 95]))
+    assert np.max(np.abs(pct - np.percentile(T, [5, 50, 95], axis=1).T)) < 2 * 30 / 1024
+    mean, std = S.mean_std(mom, T.shape[1])
+    np.testing.assert_allclose(mean, T.mean(axis=1), rtol=1e-12)
+    np.testing.assert_allclose(std, T.std(axis=1), rtol=1e-9)
+
+
+def test_shape_validation():
+    sh = conc._shapes
+    assert sh((3, 10, 8), (3, 17, 8), (4, 8), None, None, False) == (3, 10, 8, False, 1, 0)
+    assert sh((3, 10, 4), (3, 17, 8), (4, 8), object(), (10, 4), False)[3:] == (True, 4, 1)
+    assert sh((3, 10, 8), (3, 17, 8), (4, 8), None, (10, 8), True)[5] == 2
+    with pytest.raises(ValueError):
+        sh((3, 10, 8), (2, 17, 8), (4, 8), None, None, False)
+    with pytest.raises(ValueError):
+        sh((5, 10, 8), (5, 17, 8), (4, 8), None, None, False)
+    with pytest.raises(ValueError):
+        sh((3, 10, 8), (3, 17, 8), (4, 8), None, (9,), False)
+    with pytest.raises(ValueError):
+        conc._build_desc(3, 1, 1, 2, 1, False, 0, "exp", 0, "sideways", ("T",), 1.0, 100.0, None, None)
+
+
+def test_default_parameters_are_sane():
+    gp, tp = P.default_params(2)
+    assert gp.shape == (3, 17, 2) and tp.shape == (4, 2)
+    np.testing.assert_allclose(gp[:, 0:4].sum(axis=1), 1.0)
+    ens = P.sample_ensemble(100, n_t=50, dense_pools=True)
+    assert np.all(ens["gas_params"][:, 4:8] > 0) and np.all(ens["gas_params"][:, 14:17] != 0)
+    np.testing.assert_allclose(ens["gas_params"][:, 0:4].sum(axis=1), 1.0, rtol=1e-12)
+    E = P.scenario_emissions(736)
+    assert E.shape == (3, 736, 4) and abs(E[0, 255, 1] - 10.0) < 0.2       # ~10 GtC/yr in 2020
+
+
+def test_no_cpu_fallback_without_cuda():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("CUDA present")
+    ens = P.sample_ensemble(4, n_t=3)
+    E = P.member_emissions(ens["scen"], ens["scen_idx"], ens["e_scale"])
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        conc.run_ensemble(E, ens["gas_params"], ens["thermal_params"])
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        conc.calculate_hfc_conc(np.array([10, 0]), np.array([0, 1]), 1.0)
+
+
+def test_missing_library_fails_loudly(tmp_path):
+    code = textwrap.dedent(f"""
+        import sys; sys.path.insert(0, {ROOT!r})
+        from fiveeqscm_b200 import _abi
+        _abi._LIB_PATH = {str(tmp_path / 'nope.so')!r}
+        try:
+            _abi.lib()
+        except ImportError as e:
+            assert 'no CPU fallback' in str(e); print('LOUD')
+    """)
+    out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=120)
+    assert "LOUD" in out.stdout, out.stderr
+
+
+WORKER = r"""
+import os, sys
+sys.path.insert(0, {root!r})
+import numpy as np, torch, torch.distributed as dist
+from fiveeqscm_b200 import dist as D, params as P, stats as S
+from oracle import c_oracle as co
+rank, world = int(sys.argv[1]), int(sys.argv[2])
+os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=sys.argv[3], RANK=str(rank), WORLD_SIZE=str(world))
+dist.init_process_group("gloo", rank=rank, world_size=world)
+M, n_t = 1000, 40
+ens = P.sample_ensemble(M, n_t=n_t, seed=5)
+E = P.member_emissions(ens["scen"], ens["scen_idx"], ens["e_scale"])
+lo, hi = D.shard_bounds(M, world, rank)
+# each rank integrates ITS members (here with the CPU checker standing in for the GPU kernel,
+# which cannot run on this box) and builds its local statistics ...
+T = co.oxfair(E[:, :, lo:hi], ens["gas_params"][:, :, lo:hi], ens["thermal_params"][:, lo:hi])["T"]
+h, m = co.temperature_stats(T, -5.0, 25.0, 256)
+hist = torch.from_numpy(h.astype(np.int64)); mom = torch.from_numpy(m)
+# ... and the product's reduction combines them
+D.allreduce_stats(hist, mom)
+Tall = co.oxfair(E, ens["gas_params"], ens["thermal_params"])["T"]
+h_all, m_all = co.temperature_stats(Tall, -5.0, 25.0, 256)
+assert np.array_equal(hist.numpy().astype(np.uint64), h_all), "histogram not bitwise equal to single-rank"
+assert np.allclose(mom.numpy()[:, :2], m_all[:, :2], rtol=1e-12)
+assert np.array_equal(mom.numpy()[:, 2:], m_all[:, 2:])
+dist.barrier(); dist.destroy_process_group()
+print("RANK_OK", rank)
+"""
+
+
+def test_two_rank_gloo_reduction_matches_single_rank(tmp_path):
+    script = tmp_path / "worker.py"
+    script.write_text(WORKER.format(root=ROOT))
+    port = str(29500 + os.getpid() % 2000)
+    procs = [subprocess.Popen([sys.executable, str(script), str(r), "2", port], stdout=subprocess.PIPE,
+                              stderr=subprocess.PIPE, text=True) for r in range(2)]
+    for r, p in enumerate(procs):
+        out, err = p.communicate(timeout=300)
+        assert p.returncode == 0 and f"RANK_OK {r}" in out, err[-2000:]
