@@ -1,0 +1,385 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the Universal-FaIR ensemble integrator on B200.
+
+Metric (BASELINE.json): ensemble member-timesteps/sec.  Workload: one GPU's shard of configs[3]
+(10^7-member x 736-year 3-gas ensemble over 8 GPUs = 1.25e6 members per GPU), FP64, per-member
+emissions resident in HBM, full C/RF/T output to HBM, per-step temperature histogram + moments,
+NCCL all-reduce of the statistics when N > 1.  Weak scaling: per-GPU work is fixed.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W]            our arm
+    python bench.py --impl reference ...                             the CPU arm (oracle on host cores)
+    torchrun --nproc-per-node N bench.py --gpus N ...                N > 1
+
+One JSON line on stdout (rank 0).  `value` = device-resident throughput; `e2e` = the same metric
+through the public host-buffer API (pinned host inputs -> H2D -> kernel -> D2H of all outputs);
+`roofline` = the integrate kernel against the FP64-pipe peak measured in this run (and the HBM
+view); `cpu_baseline` = the C oracle timed on this box's cores on a bounded sample.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import tempfile
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+N_GAS = 3
+# algorithmic work per member-step (BASELINE.md section 5 / DESIGN.md): 3 gases
+BYTES_PER_STEP_F64 = 80.0            # 3 E in + 3 C + 3 RF + 1 T out, 8 B each
+FLOPS_PER_STEP = 751.0               # 163 simple + 15 exp(28) + 3 log(36) + 3 sqrt(10) + 3 div(10)
+METRIC = "ensemble member-timesteps/sec"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--members-per-gpu", type=int, default=1_250_000)
+    ap.add_argument("--n-t", type=int, default=736)
+    ap.add_argument("--precision", default="f64", choices=["f64", "f32"])
+    ap.add_argument("--e2e-members", type=int, default=262_144)
+    ap.add_argument("--e2e-steps", type=int, default=2)
+    ap.add_argument("--cpu-seconds", type=float, default=15.0, help="target CPU work for the cpu_baseline sample")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--sparse", action="store_true", help="literature-style sparse parameters (1-pool CH4/N2O)")
+    return ap.parse_args()
+
+
+def workload_config(args, n_gpus):
+    return {
+        "workload": "configs[3] shard: 3-gas (CO2/CH4/N2O) x %d steps x %d members per GPU (x%d GPUs = %d members), "
+                    "per-member emissions, full C/RF/T output + per-step T histogram (1024 bins) and moments"
+                    % (args.n_t, args.members_per_gpu, n_gpus, args.members_per_gpu * n_gpus),
+        "members_per_gpu": args.members_per_gpu, "n_t": args.n_t, "n_gas": N_GAS, "dt_years": 1.0,
+        "alpha_mode": "exp", "t_mode": "mid", "parameters": "sparse" if args.sparse else "dense (4 active pools, 3 forcing terms per gas)",
+        "sharding": "member axis, %d rank(s), no data-path collective; one all-reduce of histogram+moments" % n_gpus,
+        "l2": "inputs (%.1f GB per step) exceed L2; no explicit flush" % (N_GAS * args.n_t * args.members_per_gpu * 8 / 1e9),
+    }
+
+
+# ------------------------------------------------------------------------------------------------
+# synthetic inputs on the device (same recipe as fiveeqscm_b200.params, torch RNG)
+# ------------------------------------------------------------------------------------------------
+def device_ensemble(torch, M, n_t, rank, dense):
+    from fiveeqscm_b200 import _abi
+    from fiveeqscm_b200 import params as P
+    dev = torch.device("cuda", torch.cuda.current_device())
+    g = torch.Generator(device=dev).manual_seed(20261018 + 1000 * rank)
+    gp0, tp0 = _dense_table(P) if dense else P.default_params(1)   # unperturbed parameter table
+    gp =torch.from_numpy(gp0).to(dev).repeat(1, 1, M).contiguous()
+    tp = torch.from_numpy(tp0).to(dev).repeat(1, M).contiguous()
+    rn = lambda *s: torch.randn(*s, generator=g, device=dev, dtype=torch.float64)
+    ln = lambda *s: torch.exp(0.1 * rn(*s))
+    nm = lambda *s: 1.0 + 0.13 * rn(*s)
+    gp[:, _abi.GP_TAU0:_abi.GP_TAU0 + 4] *= ln(N_GAS, 4, M)
+    a = gp[:, _abi.GP_A0:_abi.GP_A0 + 4] * ln(N_GAS, 4, M)
+    gp[:, _abi.GP_A0:_abi.GP_A0 + 4] = a / a.sum(dim=1, keepdim=True)
+    gp[:, _abi.GP_R0] *= ln(N_GAS, M)
+    for row in (_abi.GP_RU, _abi.GP_RT, _abi.GP_RA):
+        gp[:, row] *= nm(N_GAS, M)
+    gp[:, _abi.GP_F1:_abi.GP_F3 + 1] *= ln(N_GAS, 3, M)
+    tp *= ln(4, M)
+    scen = torch.from_numpy(P.scenario_emissions(n_t)).to(dev)                  # [3][n_t][4]
+    idx = torch.randint(0, scen.shape[2], (M,), generator=g, device=dev)
+    scale = 1.0 + 0.05 * rn(N_GAS, M)
+    E = scen[:, :, idx]                                                           # [3][n_t][M]
+    E *= scale[:, None, :]
+    return E.contiguous(), gp, tp
+
+
+def _dense_table(P):
+    class _Z:
+        def standard_normal(self, shape):
+            return np.zeros(shape)
+    return P.sample_params(1, _Z(), dense_pools=True)
+
+
+# ------------------------------------------------------------------------------------------------
+# clocks
+# ------------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", "-i", str(index), "--query-gpu=" + self.Q,
+                                       "--format=csv,noheader,nounits", "-lms", "100"], stdout=self.f,
+                                      stderr=subprocess.DEVNULL)
+        except OSError:
+            self.p = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "power_w_max": None, "samples": 0}
+        if self.p is None:
+            return out
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.p.kill()
+        self.f.flush()
+        self.f.seek(0)
+        sm, mx, pw, reasons = [], [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in self.f.read().splitlines():
+            c = [x.strip() for x in line.split(",")]
+            if len(c) < 7:
+                continue
+            try:
+                sm.append(float(c[0])); mx.append(float(c[1])); pw.append(float(c[2]))
+            except ValueError:
+                continue
+            for nme, v in zip(names, c[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(nme)
+        self.f.close()
+        os.unlink(self.f.name)
+        if sm:
+            busy = [s for s, p in zip(sm, pw) if p > 0.5 * max(pw)] or sm
+            out.update(sm_mhz=statistics.median(busy), sm_max_mhz=max(mx), reasons=sorted(reasons),
+                       power_w_max=max(pw), samples=len(sm))
+        return out
+
+
+# ------------------------------------------------------------------------------------------------
+# CPU arm: the oracle on the host cores (the only place bench.py executes oracle/)
+# ------------------------------------------------------------------------------------------------
+def cpu_oracle_rate(E, gp, tp, target_seconds, threads=0):
+    """member-steps/s of the C oracle on a bounded sample (first members of the workload)."""
+    from oracle import c_oracle as co
+    n_thr = co.max_threads() if threads <= 0 else threads
+    n_t = E.shape[1]
+    probe = min(E.shape[2], 64 * n_thr)
+    t0 = time.perf_counter()
+    co.oxfair(E[:, :, :probe], gp[:, :, :probe], tp[:, :probe], outputs=("C", "RF", "T"), n_threads=n_thr)
+    dt0 = max(time.perf_counter() - t0, 1e-6)
+    n = int(min(E.shape[2], max(probe, probe * target_seconds / dt0)))
+    t0 = time.perf_counter()
+    out = co.oxfair(E[:, :, :n], gp[:, :, :n], tp[:, :n], outputs=("C", "RF", "T"), n_threads=n_thr)
+    dt1 = time.perf_counter() - t0
+    return n * n_t / dt1, out["threads"], n, dt1
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from fiveeqscm_b200 import params as P
+    from oracle import c_oracle as co
+    n_thr = co.max_threads()
+    n = max(256, 128 * n_thr)
+    ens = P.sample_ensemble(n, n_t=args.n_t, dense_pools=not args.sparse)
+    E = P.member_emissions(ens["scen"], ens["scen_idx"], ens["e_scale"])
+    gp, tp = ens["gas_params"], ens["thermal_params"]
+    # size each step at ~2 s of work
+    t0 = time.perf_counter()
+    co.oxfair(E, gp, tp, n_threads=n_thr)
+    dt0 = time.perf_counter() - t0
+    reps = max(1, int(2.0 / max(dt0, 1e-3)))
+    def step():
+        for _ in range(reps):
+            out = co.oxfair(E, gp, tp, n_threads=n_thr)
+            h, m = co.temperature_stats(out["T"], -5.0, 25.0, 1024)
+    for _ in range(args.warmup):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        step()
+    el = time.perf_counter() - t0
+    work = args.steps * reps * n * args.n_t
+    val = work / el
+    sample = "%d members x %d steps x %d repeats per step (C oracle, OpenMP, incl. histogram)" % (n, args.n_t, reps)
+    line = {"impl": "reference", "metric": METRIC, "value": val, "unit": "member-timesteps/s", "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * el / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": workload_config(args, args.gpus),
+            "cpu_baseline": {"value": val, "unit": "member-timesteps/s", "cores": n_thr, "kind": "port", "sample": sample,
+                             "host_cpus": os.cpu_count()},
+            "e2e": {"value": val, "unit": "member-timesteps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0,
+            "note": "the reference ships no implementation of the 5-equation loop (SURVEY.md 0); this arm times the "
+                    "in-repo C restatement (oracle/ufair_oracle.c) on the host cores"}
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------
+def main():
+    args = parse()
+    if args.impl == "reference":
+        run_reference(args)
+        return
+    import torch
+    import torch.distributed as dist
+    from fiveeqscm_b200 import _abi, concentrations as conc, dist as D
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    assert torch.cuda.is_available(), "bench.py (our arm) needs a GPU; there is no CPU fallback"
+    torch.cuda.set_device(local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    n_gpus = world
+    L = _abi.lib()
+    M, n_t = args.members_per_gpu, args.n_t
+
+    E, gp, tp = device_ensemble(torch, M, n_t, rank, dense=not args.sparse)
+    spec = conc.HistSpec()
+    plan = conc.DevicePlan(E, gp, tp, stats=spec, precision=args.precision)
+    res = plan.result
+    if args.precision == "f32":
+        pass  # DevicePlan converted the inputs; E/gp/tp (f64) are only kept for the CPU sample
+
+    ev = lambda: torch.cuda.Event(enable_timing=True)
+    kern_ev = [(ev(), ev()) for _ in range(args.steps)]
+
+    def step(i=None):
+        plan.reset_stats()
+        if i is not None:
+            kern_ev[i][0].record()
+        plan.launch()
+        if i is not None:
+            kern_ev[i][1].record()
+        plan.finalize_stats()
+        if world > 1:
+            D.allreduce_stats(res.hist, res.moments)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(args.warmup, 0)):
+        step()
+    barrier()
+    clocks = ClockSampler(local) if rank == 0 else None
+    e0, e1 = ev(), ev()
+    e0.record()
+    for i in range(args.steps):
+        step(i)
+    e1.record()
+    barrier()
+    clk = clocks.stop() if clocks else None
+    ms = torch.tensor([e0.elapsed_time(e1)], device="cuda", dtype=torch.float64)
+    kms = torch.tensor([sum(a.elapsed_time(b) for a, b in kern_ev) / args.steps], device="cuda", dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        dist.all_reduce(kms, op=dist.ReduceOp.MAX)
+    total_ms, kernel_ms = float(ms.item()), float(kms.item())
+    ms_per_step = total_ms / args.steps
+    units_per_step = float(M) * n_t * n_gpus
+    value = units_per_step / (ms_per_step * 1e-3)
+
+    # sanity on the result of the last step (cheap, outside the timed region)
+    assert bool((res.hist.sum(dim=1) == M * n_gpus).all()), "histogram rows must count every member"
+    assert bool(torch.isfinite(res.T[-1]).all())
+
+    line = {"metric": METRIC, "value": value, "unit": "member-timesteps/s", "n_gpus": n_gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": args.precision, "data": "synthetic", "config": workload_config(args, n_gpus),
+            "gpu_launches": 3 * args.steps, "kernel_ms_per_launch": kernel_ms}
+
+    if rank == 0:
+        line["clocks"] = clk
+        # ---- roofline of the dominant kernel (ufair_integrate_kernel), measured live
+        es = 8 if args.precision == "f64" else 4
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+        hbm_src = "MEASURED_PEAKS.json (measured)" if "hbm_gbs" in peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
+        msd, fl = __import__("ctypes").c_double(), __import__("ctypes").c_double()
+        peak_fn = L.ufair_peak_fp64 if args.precision == "f64" else L.ufair_peak_fp32
+        _abi.check(peak_fn(400_000 if args.precision == "f64" else 800_000, msd, fl, None))
+        fpeak = fl.value / (msd.value * 1e-3) / 1e12
+        bytes_per_launch = (N_GAS + 2 * N_GAS + 1) * es * float(M) * n_t
+        flops_per_launch = FLOPS_PER_STEP * float(M) * n_t
+        a_hbm = bytes_per_launch / (kernel_ms * 1e-3) / 1e9
+        a_fp = flops_per_launch / (kernel_ms * 1e-3) / 1e12
+        traffic = None
+        try:
+            traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get(args.precision)
+        except Exception:
+            pass
+        t_hbm, t_fp = bytes_per_launch / (hbm_peak * 1e9), flops_per_launch / (fpeak * 1e12)
+        bound = "fp64" if args.precision == "f64" else "fp32"
+        if t_hbm > t_fp:
+            roof = {"bound": "hbm", "achieved": a_hbm, "peak": hbm_peak, "unit": "GB/s", "frac": a_hbm / hbm_peak}
+        else:
+            roof = {"bound": bound, "achieved": a_fp, "peak": fpeak, "unit": "TFLOP/s", "frac": a_fp / fpeak}
+        roof.update({
+            "traffic": traffic, "kernel": "ufair_integrate_kernel<%s,3,EXP>" % ("double" if es == 8 else "float"),
+            "kernel_ms": kernel_ms, "kernel_share_of_step": kernel_ms / ms_per_step,
+            "algorithmic_bytes_per_member_step": (N_GAS + 2 * N_GAS + 1) * es,
+            "algorithmic_flops_per_member_step": FLOPS_PER_STEP,
+            "hbm": {"achieved": a_hbm, "peak": hbm_peak, "unit": "GB/s", "frac": a_hbm / hbm_peak, "peak_source": hbm_src},
+            bound: {"achieved": a_fp, "peak": fpeak, "unit": "TFLOP/s", "frac": a_fp / fpeak,
+                    "peak_source": "FMA microbenchmark in this run (ufair_peak_%s, %.1f ms)" % (bound, msd.value)},
+        })
+        line["roofline"] = roof
+
+    # ---- e2e: the public host-buffer API, pinned host inputs, H2D + kernel + D2H of every output
+    if not args.no_e2e:
+        Me = min(args.e2e_members, M)
+        pin = lambda x: x.cpu().pin_memory()
+        Eh, gph, tph = pin(E[:, :, :Me]), pin(gp[:, :, :Me]), pin(tp[:, :Me])
+        outs = ("C", "RF", "T")
+        out = conc.pinned_result(N_GAS, n_t, Me, outputs=outs, stats=spec, precision=args.precision)
+        ws = conc.Workspace(local, 65536)
+        call = lambda: conc.run_ensemble(Eh, gph, tph, stats=spec, outputs=outs, precision=args.precision,
+                                         workspace=ws, out=out)
+        call()  # warm-up: staging allocation
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(args.e2e_steps):
+            r = call()
+            if world > 1:
+                hh, mm = torch.from_numpy(r.hist).cuda(), torch.from_numpy(r.moments).cuda()
+                D.allreduce_stats(hh, mm)
+                torch.cuda.synchronize()
+        el = torch.tensor([time.perf_counter() - t0], device="cuda", dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(el, op=dist.ReduceOp.MAX)
+        es = 8 if args.precision == "f64" else 4
+        h2d = (N_GAS * n_t + N_GAS * 17 + 4) * Me * es
+        d2h = ((2 * N_GAS + 1) * n_t + 18) * Me * es + n_t * spec.bins * 8 + n_t * 32
+        line["e2e"] = {"value": float(Me) * n_t * n_gpus * args.e2e_steps / float(el.item()),
+                       "unit": "member-timesteps/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                       "members_per_gpu": Me, "steps": args.e2e_steps,
+                       "what": "run_ensemble(host pinned E/params -> all of C, RF, T, state + histogram back on the host), "
+                               "chunked 65536 members, H2D/kernel/D2H overlapped on 3 streams; wall clock, max over ranks"}
+        ws.close()
+
+    # ---- CPU baseline: the oracle on this box's cores, bounded sample of the same workload
+    if rank == 0 and not args.no_cpu:
+        n_cpu = min(M, 65536)
+        rate, thr, n_used, secs = cpu_oracle_rate(E[:, :, :n_cpu].cpu().numpy(), gp[:, :, :n_cpu].cpu().numpy(),
+                                                  tp[:, :n_cpu].cpu().numpy(), args.cpu_seconds)
+        line["cpu_baseline"] = {"value": rate, "unit": "member-timesteps/s", "cores": thr, "kind": "port",
+                                "sample": "first %d members of rank 0's shard x %d steps, C oracle with OpenMP, %.1f s"
+                                          % (n_used, n_t, secs), "host_cpus": os.cpu_count()}
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    if rank == 0:
+        print(json.dumps(line), flush=True)
+
+
+if __name__ == "__main__":
+    main()

@@ -149,7 +149,7 @@ def _build_desc(G, n_t, M, ld, n_scen, e_scen, fext_mode, alpha_mode, newton_ite
 def run_ensemble(emissions, gas_params, thermal_params, *, dt=1.0, scen_idx=None, e_scale=None, f_ext=None,
                  fext_per_member=False, state_in=None, alpha_mode="exp", newton_iters=0, iirf_max=None,
                  iirf_h=100.0, t_mode="mid", outputs: Sequence[str] = ("C", "RF", "T"), stats: Optional[HistSpec] = None,
-                 precision="f64", return_state=True, chunk_members=65536, workspace=None) -> EnsembleResult:
+                 precision="f64", return_state=True, chunk_members=65536, workspace=None, out=None) -> EnsembleResult:
     """Integrate the 5-equation model for an ensemble (oxfair, .coveragerc:19, as one kernel launch).
 
     emissions      [G][n_t][M] per-member emission RATES, or [G][n_t][S] scenario-shared with
@@ -164,7 +164,9 @@ def run_ensemble(emissions, gas_params, thermal_params, *, dt=1.0, scen_idx=None
     precision      "f64" (default; <= 1e-10 relative vs the float64 oracle) or "f32" (<= 1e-4 K in T).
 
     torch.cuda tensors -> results are torch.cuda tensors (current stream, asynchronous);
-    numpy / CPU tensors -> chunked host pipeline, results are numpy arrays.
+    numpy / CPU tensors -> chunked host pipeline, results are numpy arrays.  For repeated host
+    calls pass ``workspace=Workspace(...)`` (device staging reuse) and ``out=previous_result``
+    (host output reuse; allocate those with :func:`pinned_result` for full-speed D2H).
     """
     torch = _require_cuda()
     if precision not in ("f64", "f32"):
@@ -176,7 +178,7 @@ def run_ensemble(emissions, gas_params, thermal_params, *, dt=1.0, scen_idx=None
                            tuple(outputs), stats, precision, return_state)
     return _run_host(torch, emissions, gas_params, thermal_params, dt, scen_idx, e_scale, f_ext, fext_per_member,
                      state_in, alpha_mode, newton_iters, iirf_max, iirf_h, t_mode, tuple(outputs), stats, precision,
-                     return_state, chunk_members, workspace)
+                     return_state, chunk_members, workspace, out)
 
 
 def _shapes(E_shape, gp_shape, tp_shape, scen_idx, fext_shape, fext_per_member):
@@ -209,94 +211,129 @@ def _shapes(E_shape, gp_shape, tp_shape, scen_idx, fext_shape, fext_per_member):
     return G, n_t, M, e_scen, n_scen, fext_mode
 
 
-def _run_device(torch, E, gp, tp, dt, scen_idx, e_scale, f_ext, fext_per_member, state_in, alpha_mode, newton_iters,
-                iirf_max, iirf_h, t_mode, outputs, stats, precision, return_state):
-    L = _abi.lib()
-    dtype = torch.float64 if precision == "f64" else torch.float32
-    es = 8 if precision == "f64" else 4
-    dev = E.device
-    fshape = None if f_ext is None else tuple(f_ext.shape)
-    G, n_t, M, e_scen, n_scen, fext_mode = _shapes(tuple(E.shape), tuple(gp.shape), tuple(tp.shape), scen_idx, fshape,
-                                                   fext_per_member)
-    ld = _round_up(max(M, 1), 16 // es)
+class DevicePlan:
+    """A prepared device-resident run: descriptor + buffers.  ``run_ensemble`` on CUDA tensors is
+    ``plan = DevicePlan(...); plan.reset_stats(); plan.launch(); plan.finalize_stats()``; callers
+    that repeat the same run (benchmarks, time-chunked drivers) keep the plan and re-launch it."""
 
-    def member_rows(x, name):  # [..][M] -> contiguous [..][ld] of the run dtype, 16-byte aligned rows
-        x = torch.as_tensor(x, device=dev)
-        if x.dtype != dtype:
-            x = x.to(dtype)
-        if x.shape[-1] != M:
-            raise ValueError(f"{name}: last axis must be the member axis ({M})")
-        if ld != M:
-            x = torch.nn.functional.pad(x, (0, ld - M))
-        x = x.contiguous()
-        if x.data_ptr() % 16:
-            x = x.clone()
-        return x
+    def __init__(self, E, gp, tp, *, dt=1.0, scen_idx=None, e_scale=None, f_ext=None, fext_per_member=False,
+                 state_in=None, alpha_mode="exp", newton_iters=0, iirf_max=None, iirf_h=100.0, t_mode="mid",
+                 outputs=("C", "RF", "T"), stats=None, precision="f64", return_state=True):
+        torch = _require_cuda()
+        self._L = _abi.lib()
+        dtype = torch.float64 if precision == "f64" else torch.float32
+        es = 8 if precision == "f64" else 4
+        dev = E.device
+        self.device, self.precision, self.stats = dev, precision, stats
+        fshape = None if f_ext is None else tuple(f_ext.shape)
+        G, n_t, M, e_scen, n_scen, fext_mode = _shapes(tuple(E.shape), tuple(gp.shape), tuple(tp.shape), scen_idx,
+                                                       fshape, fext_per_member)
+        self.n_gas, self.n_t, self.n_member = G, n_t, M
+        ld = _round_up(max(M, 1), 16 // es)
 
-    def shared(x):
-        return torch.as_tensor(x, device=dev).to(dtype).contiguous()
+        def member_rows(x, name):  # [..][M] -> contiguous [..][ld] of the run dtype, 16-byte aligned rows
+            x = torch.as_tensor(x, device=dev)
+            if x.dtype != dtype:
+                x = x.to(dtype)
+            if x.shape[-1] != M:
+                raise ValueError(f"{name}: last axis must be the member axis ({M})")
+            if ld != M:
+                x = torch.nn.functional.pad(x, (0, ld - M))
+            x = x.contiguous()
+            if x.data_ptr() % 16:
+                x = x.clone()
+            return x
 
-    keep = []
-    E_d = shared(E) if e_scen else member_rows(E, "emissions")
-    gp_d, tp_d = member_rows(gp, "gas_params"), member_rows(tp, "thermal_params")
-    keep += [E_d, gp_d, tp_d]
-    d = _build_desc(G, n_t, M, ld, n_scen, e_scen, fext_mode, alpha_mode, newton_iters, t_mode, outputs, dt, iirf_h,
-                    iirf_max, stats)
-    d.emissions, d.gas_params, d.thermal_params = E_d.data_ptr(), gp_d.data_ptr(), tp_d.data_ptr()
-    if scen_idx is not None:
-        si = torch.as_tensor(scen_idx, device=dev).to(torch.int32).contiguous()
-        if si.numel() != M:
-            raise ValueError("scen_idx must have one entry per member")
-        if int(si.min()) < 0 or int(si.max()) >= n_scen:
-            raise ValueError("scen_idx out of range")
-        keep.append(si)
-        d.scen_idx = si.data_ptr()
-    if e_scale is not None:
-        if not e_scen:
-            raise ValueError("e_scale applies to scenario-shared emissions only")
-        esd = member_rows(e_scale, "e_scale")
-        keep.append(esd)
-        d.e_scale = esd.data_ptr()
-    if f_ext is not None:
-        fx = member_rows(f_ext, "f_ext") if fext_per_member else shared(f_ext)
-        if not fext_per_member and fx.numel() == n_t and n_scen > 1:
-            fx = fx.reshape(n_t, 1).expand(n_t, n_scen).contiguous()
-        keep.append(fx)
-        d.f_ext = fx.data_ptr()
-    if state_in is not None:
-        sin_ = member_rows(state_in, "state_in")
-        if sin_.shape[0] != _abi.state_rows(G):
-            raise ValueError("state_in must be [5G+3][M]")
-        keep.append(sin_)
-        d.state_in = sin_.data_ptr()
+        def shared(x):
+            return torch.as_tensor(x, device=dev).to(dtype).contiguous()
 
-    res = EnsembleResult(spec=stats, n_member=M)
-    new = lambda *shape: torch.empty(*shape, dtype=dtype, device=dev)
-    if "C" in outputs:
-        buf = new(G, n_t, ld); d.out_C = buf.data_ptr(); res.C = buf[..., :M]
-    if "RF" in outputs:
-        buf = new(G, n_t, ld); d.out_RF = buf.data_ptr(); res.RF = buf[..., :M]
-    if "T" in outputs:
-        buf = new(n_t, ld); d.out_T = buf.data_ptr(); res.T = buf[..., :M]
-    if "alpha" in outputs:
-        buf = new(G, n_t, ld); d.out_alpha = buf.data_ptr(); res.alpha = buf[..., :M]
-    if return_state:
-        buf = new(_abi.state_rows(G), ld); d.state_out = buf.data_ptr(); res.state = buf[..., :M]
-    stream = torch.cuda.current_stream(dev).cuda_stream
-    run = L.ufair_run_f64 if precision == "f64" else L.ufair_run_f32
-    with torch.cuda.device(dev):
+        keep = []
+        E_d = shared(E) if e_scen else member_rows(E, "emissions")
+        gp_d, tp_d = member_rows(gp, "gas_params"), member_rows(tp, "thermal_params")
+        keep += [E_d, gp_d, tp_d]
+        d = _build_desc(G, n_t, M, ld, n_scen, e_scen, fext_mode, alpha_mode, newton_iters, t_mode, outputs, dt,
+                        iirf_h, iirf_max, stats)
+        d.emissions, d.gas_params, d.thermal_params = E_d.data_ptr(), gp_d.data_ptr(), tp_d.data_ptr()
+        if scen_idx is not None:
+            si = torch.as_tensor(scen_idx, device=dev).to(torch.int32).contiguous()
+            if si.numel() != M:
+                raise ValueError("scen_idx must have one entry per member")
+            if M and (int(si.min()) < 0 or int(si.max()) >= n_scen):
+                raise ValueError("scen_idx out of range")
+            keep.append(si)
+            d.scen_idx = si.data_ptr()
+        if e_scale is not None:
+            if not e_scen:
+                raise ValueError("e_scale applies to scenario-shared emissions only")
+            esd = member_rows(e_scale, "e_scale")
+            keep.append(esd)
+            d.e_scale = esd.data_ptr()
+        if f_ext is not None:
+            fx = member_rows(f_ext, "f_ext") if fext_per_member else shared(f_ext)
+            if not fext_per_member and fx.numel() == n_t and n_scen > 1:
+                fx = fx.reshape(n_t, 1).expand(n_t, n_scen).contiguous()
+            keep.append(fx)
+            d.f_ext = fx.data_ptr()
+        if state_in is not None:
+            sin_ = member_rows(state_in, "state_in")
+            if sin_.shape[0] != _abi.state_rows(G):
+                raise ValueError("state_in must be [5G+3][M]")
+            keep.append(sin_)
+            d.state_in = sin_.data_ptr()
+
+        res = EnsembleResult(spec=stats, n_member=M)
+        new = lambda *shape: torch.empty(*shape, dtype=dtype, device=dev)
+        if "C" in outputs:
+            buf = new(G, n_t, ld); d.out_C = buf.data_ptr(); res.C = buf[..., :M]
+        if "RF" in outputs:
+            buf = new(G, n_t, ld); d.out_RF = buf.data_ptr(); res.RF = buf[..., :M]
+        if "T" in outputs:
+            buf = new(n_t, ld); d.out_T = buf.data_ptr(); res.T = buf[..., :M]
+        if "alpha" in outputs:
+            buf = new(G, n_t, ld); d.out_alpha = buf.data_ptr(); res.alpha = buf[..., :M]
+        if return_state:
+            buf = new(_abi.state_rows(G), ld); d.state_out = buf.data_ptr(); res.state = buf[..., :M]
         if stats is not None:
-            hp = torch.empty(stats.copies, n_t, stats.bins, dtype=torch.int32, device=dev)
-            mp = torch.empty(stats.copies, n_t, _abi.MOM_COUNT, dtype=torch.float64, device=dev)
-            d.hist_private, d.moments_private = hp.data_ptr(), mp.data_ptr()
-            _abi.check(L.ufair_stats_reset(C.byref(d), stream))
-        _abi.check(run(C.byref(d), stream))
-        if stats is not None:
+            self._hp = torch.empty(stats.copies, n_t, stats.bins, dtype=torch.int32, device=dev)
+            self._mp = torch.empty(stats.copies, n_t, _abi.MOM_COUNT, dtype=torch.float64, device=dev)
+            d.hist_private, d.moments_private = self._hp.data_ptr(), self._mp.data_ptr()
             res.hist = torch.empty(n_t, stats.bins, dtype=torch.int64, device=dev)
             res.moments = torch.empty(n_t, _abi.MOM_COUNT, dtype=torch.float64, device=dev)
-            _abi.check(L.ufair_stats_finalize(C.byref(d), res.hist.data_ptr(), res.moments.data_ptr(), stream))
-    res._keep = keep  # inputs stay alive until the caller drops the result
-    return res
+        res._keep = keep  # inputs stay alive as long as the result does
+        self.desc, self.result, self._keep = d, res, keep
+        self._run = self._L.ufair_run_f64 if precision == "f64" else self._L.ufair_run_f32
+
+    def _stream(self):
+        return _torch().cuda.current_stream(self.device).cuda_stream
+
+    def reset_stats(self):
+        if self.stats is not None:
+            _abi.check(self._L.ufair_stats_reset(C.byref(self.desc), self._stream()))
+
+    def launch(self):
+        """One launch of the fused integrator on the current stream (asynchronous)."""
+        _abi.check(self._run(C.byref(self.desc), self._stream()))
+
+    def finalize_stats(self):
+        if self.stats is not None:
+            r = self.result
+            _abi.check(self._L.ufair_stats_finalize(C.byref(self.desc), r.hist.data_ptr(), r.moments.data_ptr(),
+                                                    self._stream()))
+
+    def run(self) -> EnsembleResult:
+        with _torch().cuda.device(self.device):
+            self.reset_stats()
+            self.launch()
+            self.finalize_stats()
+        return self.result
+
+
+def _run_device(torch, E, gp, tp, dt, scen_idx, e_scale, f_ext, fext_per_member, state_in, alpha_mode, newton_iters,
+                iirf_max, iirf_h, t_mode, outputs, stats, precision, return_state):
+    return DevicePlan(E, gp, tp, dt=dt, scen_idx=scen_idx, e_scale=e_scale, f_ext=f_ext,
+                      fext_per_member=fext_per_member, state_in=state_in, alpha_mode=alpha_mode,
+                      newton_iters=newton_iters, iirf_max=iirf_max, iirf_h=iirf_h, t_mode=t_mode, outputs=outputs,
+                      stats=stats, precision=precision, return_state=return_state).run()
 
 
 class Workspace:
@@ -319,7 +356,7 @@ class Workspace:
 
 
 def _run_host(torch, E, gp, tp, dt, scen_idx, e_scale, f_ext, fext_per_member, state_in, alpha_mode, newton_iters,
-              iirf_max, iirf_h, t_mode, outputs, stats, precision, return_state, chunk_members, workspace):
+              iirf_max, iirf_h, t_mode, outputs, stats, precision, return_state, chunk_members, workspace, out=None):
     L = _abi.lib()
     npdt = np.float64 if precision == "f64" else np.float32
 
@@ -356,22 +393,32 @@ def _run_host(torch, E, gp, tp, dt, scen_idx, e_scale, f_ext, fext_per_member, s
         if state_in.shape != (_abi.state_rows(G), M):
             raise ValueError("state_in must be [5G+3][M]")
         d.state_in = state_in.ctypes.data
-    res = EnsembleResult(spec=stats, n_member=M)
+    res = out if out is not None else EnsembleResult()
+    res.spec, res.n_member = stats, M
+
+    def host_out(name, shape, dtype):
+        cur = getattr(res, name)
+        if isinstance(cur, torch.Tensor):
+            cur = cur.numpy()
+        if not (isinstance(cur, np.ndarray) and cur.shape == shape and cur.dtype == dtype and cur.flags.c_contiguous):
+            cur = np.empty(shape, dtype=dtype)
+        setattr(res, name, cur)
+        return cur.ctypes.data
+
     if "C" in outputs:
-        res.C = np.empty((G, n_t, M), dtype=npdt); d.out_C = res.C.ctypes.data
+        d.out_C = host_out("C", (G, n_t, M), npdt)
     if "RF" in outputs:
-        res.RF = np.empty((G, n_t, M), dtype=npdt); d.out_RF = res.RF.ctypes.data
+        d.out_RF = host_out("RF", (G, n_t, M), npdt)
     if "T" in outputs:
-        res.T = np.empty((n_t, M), dtype=npdt); d.out_T = res.T.ctypes.data
+        d.out_T = host_out("T", (n_t, M), npdt)
     if "alpha" in outputs:
-        res.alpha = np.empty((G, n_t, M), dtype=npdt); d.out_alpha = res.alpha.ctypes.data
+        d.out_alpha = host_out("alpha", (G, n_t, M), npdt)
     if return_state:
-        res.state = np.empty((_abi.state_rows(G), M), dtype=npdt); d.state_out = res.state.ctypes.data
+        d.state_out = host_out("state", (_abi.state_rows(G), M), npdt)
     hist_p = mom_p = None
     if stats is not None:
-        res.hist = np.zeros((n_t, stats.bins), dtype=np.int64)
-        res.moments = np.zeros((n_t, _abi.MOM_COUNT), dtype=np.float64)
-        hist_p, mom_p = res.hist.ctypes.data, res.moments.ctypes.data
+        hist_p = host_out("hist", (n_t, stats.bins), np.int64)
+        mom_p = host_out("moments", (n_t, _abi.MOM_COUNT), np.float64)
     own = workspace is None
     ws = Workspace(torch.cuda.current_device(), chunk_members) if own else workspace
     try:
@@ -381,3 +428,26 @@ def _run_host(torch, E, gp, tp, dt, scen_idx, e_scale, f_ext, fext_per_member, s
         if own:
             ws.close()
     return res
+
+
+def pinned_result(n_gas, n_t, n_member, outputs=("C", "RF", "T"), stats: Optional[HistSpec] = None, precision="f64",
+                  return_state=True) -> EnsembleResult:
+    """Page-locked host output buffers for :func:`run_ensemble` ``out=`` (D2H at full PCIe speed)."""
+    torch = _require_cuda()
+    dt = torch.float64 if precision == "f64" else torch.float32
+    pin = lambda *shape, dtype=dt: torch.empty(*shape, dtype=dtype, pin_memory=True).numpy()
+    r = EnsembleResult(spec=stats, n_member=n_member)
+    if "C" in outputs:
+        r.C = pin(n_gas, n_t, n_member)
+    if "RF" in outputs:
+        r.RF = pin(n_gas, n_t, n_member)
+    if "T" in outputs:
+        r.T = pin(n_t, n_member)
+    if "alpha" in outputs:
+        r.alpha = pin(n_gas, n_t, n_member)
+    if return_state:
+        r.state = pin(_abi.state_rows(n_gas), n_member)
+    if stats is not None:
+        r.hist = pin(n_t, stats.bins, dtype=torch.int64)
+        r.moments = pin(n_t, _abi.MOM_COUNT, dtype=torch.float64)
+    return r
