@@ -92,7 +92,8 @@ class UfairError(RuntimeError):
 
 
 _LIB = None
-_LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "libufair.so")
+# UFAIR_LIB selects a tuning variant of the same library (perf experiments); default: the in-tree build
+_LIB_PATH = os.environ.get("UFAIR_LIB") or os.path.join(os.path.dirname(os.path.abspath(__file__)), "libufair.so")
 
 # every symbol include/ufair.h declares, with (restype, argtypes)
 _vp, _i32, _i64, _dbl = C.c_void_p, C.c_int32, C.c_int64, C.c_double

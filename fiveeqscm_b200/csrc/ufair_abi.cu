@@ -84,9 +84,9 @@ template <typename Real> static KArgs<Real> make_args(const ufair_desc* d) {
   a.stats = d->stats;
   a.newton_iters = d->newton_iters;
   a.clamp = (d->iirf_max > 0.0 && isfinite(d->iirf_max)) ? 1 : 0;
-  a.dt = (Real)d->dt;
-  a.h = (Real)d->iirf_h;
-  a.iirf_max = (Real)d->iirf_max;
+  a.dt = d->dt;
+  a.h = d->iirf_h;
+  a.iirf_max = d->iirf_max;
   a.E = (const Real*)d->emissions;
   a.scen_idx = d->scen_idx;
   a.e_scale = (const Real*)d->e_scale;
@@ -302,7 +302,7 @@ extern "C" {
 
 int ufair_abi_version(void) { return UFAIR_ABI_VERSION; }
 const char* ufair_last_error(void) { return g_err; }
-int64_t ufair_block_members(void) { return kBlock; }
+int64_t ufair_block_members(void) { return kMemb; }
 
 int ufair_run_f64(const ufair_desc* d, void* stream) { return run_device<double>(d, (cudaStream_t)stream); }
 int ufair_run_f32(const ufair_desc* d, void* stream) { return run_device<float>(d, (cudaStream_t)stream); }

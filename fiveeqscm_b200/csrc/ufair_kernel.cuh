@@ -1,18 +1,26 @@
 // ufair_kernel.cuh -- the fused Universal-FaIR time-stepping kernel (sm_100a).
 //
-// One thread = one ensemble member.  Pool / cumulative-emission / thermal state and all
-// per-member derived parameters live in registers across the serial time loop; the loop body is
-// alpha_val -> step_conc -> step_forc -> step_temp (the names the reference reserves in
-// .coveragerc:12-19) fused, i.e. `oxfair` is ONE launch.
+// Work decomposition (v2): one WARP = 32 consecutive ensemble members of ONE gas.
+//   A CTA owns MEMB = 32*W members and has NGAS*W warps; the NGAS warps that share a 32-member
+//   group meet once per time step at a named barrier to exchange their radiative forcings through
+//   shared memory.  Every thread keeps its gas's four pools, cumulative emissions, derived
+//   parameters and (redundantly, bit-identically in the NGAS threads of a member) the two thermal
+//   boxes in REGISTERS across the serial time loop.  Compared with one thread per member this
+//   cuts registers per thread ~3x, which is what buys the 16+ resident warps per SM the FP64 pipe
+//   needs to stay fed: the loop is a chain of dependent DFMAs (Horner polynomials), so it is
+//   latency-bound unless enough independent warps interleave (ncu on v1: 2 warps/SMSP,
+//   stall_wait 3.3 cycles per issue, FP64 pipe 35 % busy -- profiles/r1_v1_summary.md).
+//   The loop body is alpha_val -> step_conc -> step_forc -> (exchange) -> step_temp, the names the
+//   reference reserves in .coveragerc:12-19; `oxfair` is ONE launch.
 //
 // Memory system
 //   * per-member emissions [gas][t][member] (and per-member external forcing) are streamed into
 //     shared memory one tile of TT time steps ahead with TMA bulk copies
-//     (cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes, one row of
-//     BLOCK members per (gas, t)), double-buffered on two mbarriers; each thread then reads its own
-//     column with a conflict-free LDS.
-//   * C / RF / T rows are written straight from registers with streaming (st.global.cs) stores,
-//     one fully-coalesced BLOCK*sizeof(Real)-byte run per row -- nothing is re-read.
+//     (cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes, one row of MEMB members
+//     per (gas, t)), double-buffered on two mbarriers; each thread reads its own column
+//     (conflict-free LDS).
+//   * C / RF / T rows are written straight from registers with streaming (st.global.cs) stores;
+//     each warp store covers one full, aligned 256-byte (f64) run -- nothing is re-read.
 //   * optional statistics: each tile's T values are staged in shared memory and folded by the
 //     whole CTA into privatised per-step histograms (RED.ADD.U32) and moments (warp-shuffle
 //     reduction, then one RED per warp-row).
@@ -23,18 +31,30 @@
 #include "../../include/ufair.h"
 #include "ufair_math.cuh"
 
+#ifndef UFAIR_MEMB
+#define UFAIR_MEMB 64  // members per CTA (multiple of 32)
+#endif
+#ifndef UFAIR_MINB_F64
+#define UFAIR_MINB_F64 3  // resident CTAs per SM the register allocator must allow (3-gas shape)
+#endif
+#ifndef UFAIR_MINB_F32
+#define UFAIR_MINB_F32 5
+#endif
+
 namespace ufair {
 
-constexpr int kBlock = 128;  // members per CTA
-constexpr int kTT = 4;       // time steps per shared-memory tile
-constexpr int kStages = 2;   // tile ring depth
+constexpr int kMemb = UFAIR_MEMB;  // members per CTA
+constexpr int kW = kMemb / 32;     // 32-member groups per CTA
+constexpr int kTT = 4;             // time steps per shared-memory tile
+constexpr int kStages = 2;         // tile ring depth
+static_assert(kMemb % 32 == 0 && kW >= 1 && kW <= 8, "UFAIR_MEMB must be 32..256 in steps of 32");
 
 template <typename Real> struct KArgs {
   int n_gas, n_t;
   long long n_member, ld;
   int n_scen;
   int e_mode, fext_mode, t_mode, out_mask, stats, newton_iters, clamp;
-  Real dt, h, iirf_max;
+  double dt, h, iirf_max;
   const Real* E;
   const int* scen_idx;
   const Real* e_scale;
@@ -53,7 +73,7 @@ template <typename Real> struct KArgs {
   double* mom;
 };
 
-// ---- small PTX wrappers: mbarrier + TMA bulk copy -------------------------------------------
+// ---- small PTX wrappers: mbarrier + TMA bulk copy + named barrier -----------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
   return static_cast<uint32_t>(__cvta_generic_to_shared(p));
 }
@@ -84,6 +104,9 @@ __device__ __forceinline__ void tma_load_row(void* smem_dst, const void* gmem_sr
 __device__ __forceinline__ void fence_barrier_init() {
   asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
 }
+__device__ __forceinline__ void named_bar_sync(int id, int count) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory");
+}
 
 template <typename Real> __device__ __forceinline__ void st_stream(Real* p, Real v) { __stcs(p, v); }
 
@@ -103,28 +126,32 @@ __host__ __device__ __forceinline__ double dec_ordered(unsigned long long u) {
 #endif
 }
 
-// ---- per-gas register state --------------------------------------------------------------------
-template <typename Real, int AMODE> struct Gas {
-  // derived per-member constants
-  Real kA[4];   // c a_i tau_i                      (equilibrium pool per unit E alpha)
-  Real k[4];    // dt / tau_i   (ALPHA_ONE: holds m_i = 1 - exp(-dt/tau_i) instead)
-  Real rho0, rhoU, wR, rhoT, umax;  // u = rho0 + rhoU Gcum + wR sumR + rhoT T  (= iIRF/g1 [+ ln g0])
-  Real C0, invC0, sqrtC0, f1, f2, f3;
-  // only some alpha modes
-  Real g0;      // SINH
-  Real g1, lng0, invc;  // NEWTON
-  // state
-  Real R[4], Gcum, sumR;
+template <typename Real, int NGAS> struct SmemLayout {
+  static constexpr size_t tile_elems = (size_t)kStages * kTT * (NGAS + 1) * kMemb;  // E (+f_ext) ring
+  static constexpr size_t ttile_elems = (size_t)2 * kTT * kMemb;                    // T staging (stats)
+  static constexpr size_t fx_elems = (size_t)2 * NGAS * kMemb;                      // forcing exchange
+  static constexpr size_t bytes = sizeof(Real) * (tile_elems + ttile_elems + fx_elems) + kStages * sizeof(uint64_t);
 };
 
+// resident CTAs per SM requested from the register allocator, scaled so that the resident THREAD
+// count stays the same for every gas count (a CTA has NGAS * MEMB threads)
+constexpr int min_blocks(int elem_size, int n_gas) {
+  const int b = (elem_size == 8 ? UFAIR_MINB_F64 : UFAIR_MINB_F32) * 3 / n_gas;
+  return b < 1 ? 1 : b;
+}
+
 template <typename Real, int NGAS, int AMODE>
-__global__ void __launch_bounds__(kBlock, (sizeof(Real) == 8 ? 2 : 4))
-ufair_integrate_kernel(const __grid_constant__ KArgs<Real> a) {
+__global__ void __launch_bounds__(NGAS* kMemb, min_blocks(sizeof(Real), NGAS))
+    ufair_integrate_kernel(const __grid_constant__ KArgs<Real> a) {
   using M = Math<Real>;
   extern __shared__ __align__(128) unsigned char smem_raw[];
   const int tid = threadIdx.x;
-  const long long m0 = (long long)blockIdx.x * kBlock;
-  const long long m_raw = m0 + tid;
+  const int lane = tid & 31, warp = tid >> 5;
+  const int mg = warp % kW;  // 32-member group inside the CTA
+  const int g = warp / kW;   // this warp's gas
+  const int j = mg * 32 + lane;
+  const long long m0 = (long long)blockIdx.x * kMemb;
+  const long long m_raw = m0 + j;
   const bool active = m_raw < a.n_member;
   const long long m = active ? m_raw : (a.n_member - 1);  // idle lanes shadow the last member
   const long long ld = a.ld;
@@ -132,16 +159,18 @@ ufair_integrate_kernel(const __grid_constant__ KArgs<Real> a) {
 
   const bool e_member = (a.e_mode == UFAIR_E_MEMBER);
   const bool fx_member = (a.fext_mode == UFAIR_FEXT_MEMBER);
+  const bool fx_scen = (a.fext_mode == UFAIR_FEXT_SCENARIO);
   const int n_row = (e_member ? NGAS : 0) + (fx_member ? 1 : 0);  // rows per time step in a tile
   const int fx_row = e_member ? NGAS : 0;
 
-  // shared memory carve-up: [stages][kTT][n_row][kBlock] E tile | [2][kTT][kBlock] T tile | mbarriers
+  using SL = SmemLayout<Real, NGAS>;
   Real* tile = reinterpret_cast<Real*>(smem_raw);
-  Real* ttile = tile + (size_t)kStages * kTT * (NGAS + 1) * kBlock;
-  uint64_t* full = reinterpret_cast<uint64_t*>(ttile + 2 * kTT * kBlock);
+  Real* ttile = tile + SL::tile_elems;
+  Real* fxch = ttile + SL::ttile_elems;
+  uint64_t* full = reinterpret_cast<uint64_t*>(fxch + SL::fx_elems);
 
-  const int valid_cols = (int)min((long long)kBlock, ld - m0);       // columns that exist in memory
-  const uint32_t row_bytes = (uint32_t)valid_cols * sizeof(Real);    // multiple of 16 (ld % (16/sizeof) == 0)
+  const int valid_cols = (int)min((long long)kMemb, ld - m0);      // columns that exist in memory
+  const uint32_t row_bytes = (uint32_t)valid_cols * sizeof(Real);  // multiple of 16 (ld % (16/sizeof) == 0)
   const int n_tile = (n_t + kTT - 1) / kTT;
 
   if (tid == 0) {
@@ -155,114 +184,113 @@ ufair_integrate_kernel(const __grid_constant__ KArgs<Real> a) {
     const int t0 = k * kTT;
     const int nt = min(kTT, n_t - t0);
     mbar_expect_tx(&full[s], (uint32_t)(nt * n_row) * row_bytes);
-    Real* dst = tile + (size_t)s * kTT * (NGAS + 1) * kBlock;
+    Real* dst = tile + (size_t)s * kTT * (NGAS + 1) * kMemb;
     for (int tt = 0; tt < nt; ++tt) {
       if (e_member) {
 #pragma unroll
-        for (int g = 0; g < NGAS; ++g)
-          tma_load_row(dst + (tt * (NGAS + 1) + g) * kBlock, a.E + ((long long)g * n_t + (t0 + tt)) * ld + m0,
+        for (int gg = 0; gg < NGAS; ++gg)
+          tma_load_row(dst + (tt * (NGAS + 1) + gg) * kMemb, a.E + ((long long)gg * n_t + (t0 + tt)) * ld + m0,
                        row_bytes, &full[s]);
       }
       if (fx_member)
-        tma_load_row(dst + (tt * (NGAS + 1) + fx_row) * kBlock, a.fext + (long long)(t0 + tt) * ld + m0, row_bytes,
+        tma_load_row(dst + (tt * (NGAS + 1) + fx_row) * kMemb, a.fext + (long long)(t0 + tt) * ld + m0, row_bytes,
                      &full[s]);
     }
   };
   if (n_row > 0 && tid == 0 && n_tile > 0) issue_tile(0);
 
-  // ---------------- prologue: raw parameters -> derived constants (g_1, g_0 fused here) --------
-  Gas<Real, AMODE> gas[NGAS];
-  const Real dt = a.dt, h = a.h;
-#pragma unroll
-  for (int g = 0; g < NGAS; ++g) {
+  // ---------------- prologue: raw parameters -> derived constants, in double for both precisions
+  // (g_1 and g_0 of .coveragerc:15-16 are fused here; in FP32 they would cancel catastrophically
+  // for the 10^6-year pool, so the one-off prologue always runs in FP64 and rounds once)
+  Real kA[4];  // c a_i tau_i               (equilibrium pool per unit E*alpha)
+  Real kk[4];  // dt / tau_i                (ALPHA_ONE: m_i = 1 - exp(-dt/tau_i) instead)
+  Real rho0, rhoU, wR, rhoT, umax;  // u = rho0 + rhoU Gcum + wR sumR + rhoT T   (= iIRF/g1 [+ ln g0])
+  Real C0, invC0, sqrtC0, f1, f2, f3;
+  Real g0s = 0, g1n = 0, lng0n = 0, invcn = 0;  // SINH: g0; NEWTON: g1, ln g0, 1/c
+  Real R[4], Gcum, sumR;
+  {
     const Real* p = a.gp + (long long)g * UFAIR_GP_COUNT * ld + m;
-    Real av[4], tau[4];
+    double av[4], tau[4];
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
-      av[i] = p[(UFAIR_GP_A0 + i) * ld];
-      tau[i] = p[(UFAIR_GP_TAU0 + i) * ld];
+      av[i] = (double)p[(UFAIR_GP_A0 + i) * ld];
+      tau[i] = (double)p[(UFAIR_GP_TAU0 + i) * ld];
     }
-    const Real r0 = p[UFAIR_GP_R0 * ld], rU = p[UFAIR_GP_RU * ld], rT = p[UFAIR_GP_RT * ld], rA = p[UFAIR_GP_RA * ld];
-    const Real C0 = p[UFAIR_GP_C0 * ld], c = p[UFAIR_GP_EMIS2CONC * ld];
-    Gas<Real, AMODE>& G = gas[g];
-    // g_1, g_0 (.coveragerc:15-16), in log form: ln g0 = -sum a tau (1 - e^{-h/tau}) / g1
-    Real g1 = 0, sden = 0;
+    const double r0 = p[UFAIR_GP_R0 * ld], rU = p[UFAIR_GP_RU * ld], rT = p[UFAIR_GP_RT * ld], rA = p[UFAIR_GP_RA * ld];
+    const double C0d = p[UFAIR_GP_C0 * ld], c = p[UFAIR_GP_EMIS2CONC * ld];
+    double g1 = 0.0, sden = 0.0;
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
-      const Real z = h / tau[i];
-      const Real ez = M::exp_ref(-z);
-      g1 += av[i] * tau[i] * (Real(1) - (Real(1) + z) * ez);
-      sden += av[i] * tau[i] * (Real(1) - ez);
+      const double z = a.h / tau[i];
+      const double ez = exp(-z);
+      g1 += av[i] * tau[i] * (1.0 - (1.0 + z) * ez);
+      sden += av[i] * tau[i] * (1.0 - ez);
     }
-    const Real sarg = sden / g1;
-    const Real inv_g1 = Real(1) / g1;
-    const Real invc = Real(1) / c;
+    const double sarg = sden / g1;
+    const double inv_g1 = 1.0 / g1, invc = 1.0 / c;
+    const double lng0 = -sarg;
+    const double fold = (AMODE == UFAIR_ALPHA_SINH) ? 0.0 : lng0;
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
-      G.kA[i] = c * av[i] * tau[i];
-      G.k[i] = (AMODE == UFAIR_ALPHA_ONE) ? M::decay(dt / tau[i]) : dt / tau[i];
+      kA[i] = (Real)(c * av[i] * tau[i]);
+      kk[i] = (Real)((AMODE == UFAIR_ALPHA_ONE) ? -expm1(-a.dt / tau[i]) : a.dt / tau[i]);
     }
-    const Real lng0 = -sarg;
-    G.rho0 = r0 * inv_g1 + ((AMODE == UFAIR_ALPHA_SINH) ? Real(0) : lng0);
-    G.rhoU = rU * inv_g1;
-    G.wR = (rA - rU) * inv_g1 * invc;
-    G.rhoT = rT * inv_g1;
-    G.umax = a.clamp ? (a.iirf_max * inv_g1 + ((AMODE == UFAIR_ALPHA_SINH) ? Real(0) : lng0)) : Real(INFINITY);
-    G.C0 = C0;
-    G.invC0 = Real(1) / C0;
-    G.sqrtC0 = sqrt(C0);
-    G.f1 = p[UFAIR_GP_F1 * ld];
-    G.f2 = p[UFAIR_GP_F2 * ld];
-    G.f3 = p[UFAIR_GP_F3 * ld];
-    G.g0 = (AMODE == UFAIR_ALPHA_SINH) ? Real(1) / sinh(sarg) : Real(0);
-    G.g1 = g1;
-    G.lng0 = lng0;
-    G.invc = invc;
+    rho0 = (Real)(r0 * inv_g1 + fold);
+    rhoU = (Real)(rU * inv_g1);
+    wR = (Real)((rA - rU) * inv_g1 * invc);
+    rhoT = (Real)(rT * inv_g1);
+    umax = a.clamp ? (Real)(a.iirf_max * inv_g1 + fold) : (Real)INFINITY;
+    C0 = (Real)C0d;
+    invC0 = (Real)(1.0 / C0d);
+    sqrtC0 = (Real)sqrt(C0d);
+    f1 = p[UFAIR_GP_F1 * ld];
+    f2 = p[UFAIR_GP_F2 * ld];
+    f3 = p[UFAIR_GP_F3 * ld];
+    if (AMODE == UFAIR_ALPHA_SINH) g0s = (Real)(1.0 / sinh(sarg));
+    if (AMODE == UFAIR_ALPHA_NEWTON) {
+      g1n = (Real)g1;
+      lng0n = (Real)lng0;
+      invcn = (Real)invc;
+    }
     if (a.state_in) {
 #pragma unroll
-      for (int i = 0; i < 4; ++i) G.R[i] = a.state_in[(long long)(5 * g + i) * ld + m];
-      G.Gcum = a.state_in[(long long)(5 * g + 4) * ld + m];
+      for (int i = 0; i < 4; ++i) R[i] = a.state_in[(long long)(5 * g + i) * ld + m];
+      Gcum = a.state_in[(long long)(5 * g + 4) * ld + m];
     } else {
 #pragma unroll
-      for (int i = 0; i < 4; ++i) G.R[i] = 0;
-      G.Gcum = 0;
+      for (int i = 0; i < 4; ++i) R[i] = 0;
+      Gcum = 0;
     }
-    G.sumR = (G.R[0] + G.R[1]) + (G.R[2] + G.R[3]);
+    sumR = (R[0] + R[1]) + (R[2] + R[3]);
   }
   Real qm[2], dec[2], S[2], Tprev;
   {
     const Real* tp = a.tp + m;
 #pragma unroll
-    for (int j = 0; j < 2; ++j) {
-      const Real q = tp[(UFAIR_TP_Q1 + j) * ld], d = tp[(UFAIR_TP_D1 + j) * ld];
-      const Real mj = M::decay(dt / d);
-      qm[j] = q * mj;
-      dec[j] = Real(1) - mj;
-      S[j] = a.state_in ? a.state_in[(long long)(5 * NGAS + j) * ld + m] : Real(0);
+    for (int i = 0; i < 2; ++i) {
+      const double q = tp[(UFAIR_TP_Q1 + i) * ld], d = tp[(UFAIR_TP_D1 + i) * ld];
+      const double mj = -expm1(-a.dt / d);
+      qm[i] = (Real)(q * mj);
+      dec[i] = (Real)(1.0 - mj);
+      S[i] = a.state_in ? a.state_in[(long long)(5 * NGAS + i) * ld + m] : Real(0);
     }
     Tprev = a.state_in ? a.state_in[(long long)(5 * NGAS + 2) * ld + m] : Real(0);
   }
   const int scen = (a.scen_idx != nullptr) ? a.scen_idx[m] : 0;
-  Real esc[NGAS];
-#pragma unroll
-  for (int g = 0; g < NGAS; ++g) esc[g] = (!e_member && a.e_scale) ? a.e_scale[(long long)g * ld + m] : Real(1);
-  const bool fx_scen = (a.fext_mode == UFAIR_FEXT_SCENARIO);
-  const Real hdt = h / dt;
+  const Real esc = (!e_member && a.e_scale) ? a.e_scale[(long long)g * ld + m] : Real(1);
+  const Real dt = (Real)a.dt;
+  const Real hdt = (Real)(a.h / a.dt);
 
   const bool wC = (a.out_mask & UFAIR_OUT_C) && active, wRF = (a.out_mask & UFAIR_OUT_RF) && active;
-  const bool wT = (a.out_mask & UFAIR_OUT_T) && active, wA = (a.out_mask & UFAIR_OUT_ALPHA) && active;
-  const long long gas_stride = (long long)n_t * ld;
+  const bool wT = (a.out_mask & UFAIR_OUT_T) && active && (g == 0), wA = (a.out_mask & UFAIR_OUT_ALPHA) && active;
+  const long long gas_off = (long long)g * n_t * ld;
   const int hist_copy = a.stats ? (int)(blockIdx.x % (unsigned)a.hist_copies) : 0;
-  const int n_valid = (int)min((long long)kBlock, a.n_member - m0);  // real members in this CTA
-  const int lane = tid & 31, warp = tid >> 5;
+  const int n_valid = (int)min((long long)kMemb, a.n_member - m0);  // real members in this CTA
+  const bool stage_T = a.stats && (g == 0);
 
-  // scenario-mode emissions: register prefetch one step ahead through the read-only path
-  Real e_next[NGAS];
-  Real fx_next = 0;
-  if (!e_member && n_t > 0) {
-#pragma unroll
-    for (int g = 0; g < NGAS; ++g) e_next[g] = __ldg(a.E + ((long long)g * n_t) * a.n_scen + scen);
-  }
+  // scenario-mode inputs: register prefetch one step ahead through the read-only path
+  Real e_next = 0, fx_next = 0;
+  if (!e_member && n_t > 0) e_next = __ldg(a.E + ((long long)g * n_t) * a.n_scen + scen);
   if (fx_scen && n_t > 0) fx_next = __ldg(a.fext + scen);
 
   // ---------------- the time loop --------------------------------------------------------------
@@ -274,117 +302,111 @@ ufair_integrate_kernel(const __grid_constant__ KArgs<Real> a) {
       if (tid == 0 && k + 1 < n_tile) issue_tile(k + 1);  // its stage was drained before the last barrier
       mbar_wait(&full[s], (uint32_t)((k / kStages) & 1));
     }
-    const Real* trow = tile + (size_t)s * kTT * (NGAS + 1) * kBlock + tid;
-    Real* tt_buf = ttile + (k & 1) * kTT * kBlock;
+    const Real* trow = tile + (size_t)s * kTT * (NGAS + 1) * kMemb + j;
+    Real* tt_buf = ttile + (k & 1) * kTT * kMemb;
 
     for (int tt = 0; tt < nt; ++tt) {
       const int t = t0 + tt;
-      Real e[NGAS];
-      Real fx = 0;
+      Real e, fx = 0;
       if (e_member) {
-#pragma unroll
-        for (int g = 0; g < NGAS; ++g) e[g] = trow[(tt * (NGAS + 1) + g) * kBlock];
+        e = trow[(tt * (NGAS + 1) + g) * kMemb];
       } else {
-        const int tn = min(t + 1, n_t - 1);
-#pragma unroll
-        for (int g = 0; g < NGAS; ++g) {
-          e[g] = e_next[g] * esc[g];
-          e_next[g] = __ldg(a.E + ((long long)g * n_t + tn) * a.n_scen + scen);
-        }
+        e = e_next * esc;
+        e_next = __ldg(a.E + ((long long)g * n_t + min(t + 1, n_t - 1)) * a.n_scen + scen);
       }
-      if (fx_member) fx = trow[(tt * (NGAS + 1) + fx_row) * kBlock];
+      if (fx_member) fx = trow[(tt * (NGAS + 1) + fx_row) * kMemb];
       if (fx_scen) {
         fx = fx_next;
         fx_next = __ldg(a.fext + (long long)min(t + 1, n_t - 1) * a.n_scen + scen);
       }
 
-      Real Ftot = fx;
-      const long long orow = (long long)t * ld + m_raw;
+      // ---- alpha_val: state at t-1 -> alpha, 1/alpha
+      Real alpha, inva;
+      if (AMODE == UFAIR_ALPHA_ONE) {
+        alpha = Real(1);
+        inva = Real(1);
+      } else {
+        Real u = fma(rhoU, Gcum, fma(wR, sumR, fma(rhoT, Tprev, rho0)));
+        u = (u > umax) ? umax : u;
+        alpha = (AMODE == UFAIR_ALPHA_SINH) ? g0s * M::sinh_pair(u) : M::exp_(u);
+        if (AMODE == UFAIR_ALPHA_NEWTON) {
+          const Real iirf = (u - lng0n) * g1n;
+          for (int it = 0; it < a.newton_iters; ++it) {
+            const Real ia = M::rcp(alpha);
+            Real f = -iirf, fp = 0;
 #pragma unroll
-      for (int g = 0; g < NGAS; ++g) {
-        Gas<Real, AMODE>& G = gas[g];
-        // ---- alpha_val: state at t-1 -> alpha, 1/alpha
-        Real alpha, inva;
-        if (AMODE == UFAIR_ALPHA_ONE) {
-          alpha = Real(1);
-          inva = Real(1);
-        } else {
-          Real u = fma(G.rhoU, G.Gcum, fma(G.wR, G.sumR, fma(G.rhoT, Tprev, G.rho0)));
-          u = (u > G.umax) ? G.umax : u;
-          if (AMODE == UFAIR_ALPHA_SINH) {
-            alpha = G.g0 * M::sinh_pair(u);
-          } else {
-            alpha = M::exp_(u);
-          }
-          if (AMODE == UFAIR_ALPHA_NEWTON) {
-            const Real iirf = (u - G.lng0) * G.g1;
-            for (int it = 0; it < a.newton_iters; ++it) {
-              const Real ia = M::rcp(alpha);
-              Real f = -iirf, fp = 0;
-#pragma unroll
-              for (int i = 0; i < 4; ++i) {
-                const Real z = G.k[i] * hdt * ia;
-                const Real mz = M::decay(z);
-                const Real at = G.kA[i] * G.invc;  // a_i tau_i
-                f = fma(at * alpha, mz, f);
-                fp = fma(at, mz - z * (Real(1) - mz), fp);
-              }
-              const Real an = alpha - f * M::rcp(fp);
-              alpha = M::fmax_(an, Real(0.5) * alpha);
+            for (int i = 0; i < 4; ++i) {
+              const Real z = kk[i] * hdt * ia;
+              const Real mz = M::decay(z);
+              const Real at = kA[i] * invcn;  // a_i tau_i
+              f = fma(at * alpha, mz, f);
+              fp = fma(at, mz - z * (Real(1) - mz), fp);
             }
+            const Real an = alpha - f * M::rcp(fp);
+            alpha = M::fmax_(an, Real(0.5) * alpha);
           }
-          inva = M::rcp(alpha);
         }
-        // ---- step_conc: relax each pool toward its equilibrium  E alpha c a_i tau_i
-        const Real ea = e[g] * alpha;
+        inva = M::rcp(alpha);
+      }
+      // ---- step_conc: relax each pool toward its equilibrium  E alpha c a_i tau_i
+      const Real ea = e * alpha;
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          const Real mi = (AMODE == UFAIR_ALPHA_ONE) ? G.k[i] : M::decay(G.k[i] * inva);
-          G.R[i] = fma(mi, fma(ea, G.kA[i], -G.R[i]), G.R[i]);
-        }
-        G.Gcum = fma(e[g], dt, G.Gcum);
-        G.sumR = (G.R[0] + G.R[1]) + (G.R[2] + G.R[3]);
-        const Real C = G.C0 + G.sumR;
-        // ---- step_forc; a zero coefficient means a zero term. Skipped only when the whole warp
-        //      agrees (parameter layouts are gas-uniform in practice, so this never diverges).
-        Real F = G.f2 * G.sumR;
-        if (__any_sync(0xffffffffu, G.f1 != Real(0))) {
-          const Real lt = G.f1 * M::log_(C * G.invC0);
-          F += (G.f1 != Real(0)) ? lt : Real(0);
-        }
-        if (__any_sync(0xffffffffu, G.f3 != Real(0))) {
-          const Real st = G.f3 * (M::sqrt_(C) - G.sqrtC0);
-          F += (G.f3 != Real(0)) ? st : Real(0);
-        }
-        Ftot += F;
-        const long long o = (long long)g * gas_stride + orow;
-        if (wC) st_stream(a.oC + o, C);
-        if (wRF) st_stream(a.oRF + o, F);
-        if (wA) st_stream(a.oA + o, alpha);
+      for (int i = 0; i < 4; ++i) {
+        const Real mi = (AMODE == UFAIR_ALPHA_ONE) ? kk[i] : M::decay(kk[i] * inva);
+        R[i] = fma(mi, fma(ea, kA[i], -R[i]), R[i]);
       }
-      // ---- step_temp
-      Real T;
-      {
-        const Real s0 = fma(qm[0], Ftot, S[0] * dec[0]);
-        const Real s1 = fma(qm[1], Ftot, S[1] * dec[1]);
-        T = (a.t_mode == UFAIR_T_MID) ? Real(0.5) * ((S[0] + s0) + (S[1] + s1)) : (s0 + s1);
-        S[0] = s0;
-        S[1] = s1;
+      Gcum = fma(e, dt, Gcum);
+      sumR = (R[0] + R[1]) + (R[2] + R[3]);
+      const Real C = C0 + sumR;
+      // ---- step_forc; a zero coefficient means a zero term.  A term is skipped only when the whole
+      //      warp agrees -- a warp holds ONE gas, so with gas-uniform parameter tables this never
+      //      diverges (CH4/N2O warps skip the log, CO2 warps the sqrt)
+      Real F = f2 * sumR;
+      if (__any_sync(0xffffffffu, f1 != Real(0))) {
+        const Real lt = f1 * M::log_(C * invC0);
+        F += (f1 != Real(0)) ? lt : Real(0);
       }
+      if (__any_sync(0xffffffffu, f3 != Real(0))) {
+        const Real st = f3 * (M::sqrt_(C) - sqrtC0);
+        F += (f3 != Real(0)) ? st : Real(0);
+      }
+      const long long orow = (long long)t * ld + m_raw;
+      if (wC) st_stream(a.oC + gas_off + orow, C);
+      if (wRF) st_stream(a.oRF + gas_off + orow, F);
+      if (wA) st_stream(a.oA + gas_off + orow, alpha);
+
+      // ---- exchange the per-gas forcings of this 32-member group (double-buffered by step parity)
+      Real* fxb = fxch + (t & 1) * NGAS * kMemb;
+      Real Ftot;
+      if (NGAS > 1) {
+        fxb[g * kMemb + j] = F;
+        named_bar_sync(1 + mg, NGAS * 32);
+        Ftot = fx;
+#pragma unroll
+        for (int gg = 0; gg < NGAS; ++gg) Ftot += fxb[gg * kMemb + j];
+      } else {
+        Ftot = fx + F;
+      }
+      // ---- step_temp (computed redundantly, bit-identically, by the NGAS threads of a member)
+      const Real s0 = fma(qm[0], Ftot, S[0] * dec[0]);
+      const Real s1 = fma(qm[1], Ftot, S[1] * dec[1]);
+      const Real T = (a.t_mode == UFAIR_T_MID) ? Real(0.5) * ((S[0] + s0) + (S[1] + s1)) : (s0 + s1);
+      S[0] = s0;
+      S[1] = s1;
       Tprev = T;
       if (wT) st_stream(a.oT + orow, T);
-      if (a.stats) tt_buf[tt * kBlock + tid] = T;
+      if (stage_T) tt_buf[tt * kMemb + j] = T;
     }
 
     __syncthreads();  // tile k fully consumed (E stage reusable) and its T values staged
 
     if (a.stats) {
-      for (int tt = warp; tt < nt; tt += kBlock / 32) {
+      for (int tt = warp; tt < nt; tt += NGAS * kW) {
         const int row = a.hist_t0 + t0 + tt;
         unsigned int* hrow = a.hist + ((size_t)hist_copy * a.hist_rows + row) * a.hist_bins;
         double sm = 0.0, ss = 0.0, mn = INFINITY, mx = -INFINITY;
-        for (int j = lane; j < n_valid; j += 32) {
-          const Real Tv = tt_buf[tt * kBlock + j];
+        for (int c = lane; c < n_valid; c += 32) {
+          const Real Tv = tt_buf[tt * kMemb + c];
           const Real x = M::bin_x(Tv, a.hist_lo, a.hist_invw);
           if (x == x) {
             const Real fl = M::floor_(x);
@@ -418,19 +440,14 @@ ufair_integrate_kernel(const __grid_constant__ KArgs<Real> a) {
   // ---------------- epilogue: final state (checkpoint / resume) ---------------------------------
   if (a.state_out && active) {
 #pragma unroll
-    for (int g = 0; g < NGAS; ++g) {
-#pragma unroll
-      for (int i = 0; i < 4; ++i) a.state_out[(long long)(5 * g + i) * ld + m] = gas[g].R[i];
-      a.state_out[(long long)(5 * g + 4) * ld + m] = gas[g].Gcum;
+    for (int i = 0; i < 4; ++i) a.state_out[(long long)(5 * g + i) * ld + m] = R[i];
+    a.state_out[(long long)(5 * g + 4) * ld + m] = Gcum;
+    if (g == 0) {
+      a.state_out[(long long)(5 * NGAS + 0) * ld + m] = S[0];
+      a.state_out[(long long)(5 * NGAS + 1) * ld + m] = S[1];
+      a.state_out[(long long)(5 * NGAS + 2) * ld + m] = Tprev;
     }
-    a.state_out[(long long)(5 * NGAS + 0) * ld + m] = S[0];
-    a.state_out[(long long)(5 * NGAS + 1) * ld + m] = S[1];
-    a.state_out[(long long)(5 * NGAS + 2) * ld + m] = Tprev;
   }
-}
-
-template <typename Real> constexpr size_t integrate_smem_bytes(int n_gas) {
-  return sizeof(Real) * ((size_t)kStages * kTT * (n_gas + 1) * kBlock + 2 * kTT * kBlock) + kStages * sizeof(uint64_t);
 }
 
 // one launcher per (Real, NGAS, AMODE); defined in ufair_inst_*.cu
@@ -438,12 +455,12 @@ template <typename Real, int NGAS, int AMODE> cudaError_t launch_integrate(const
 
 #define UFAIR_DEFINE_LAUNCH(Real, NGAS, AMODE)                                                             \
   template <> cudaError_t launch_integrate<Real, NGAS, AMODE>(const KArgs<Real>& a, cudaStream_t stream) { \
-    const size_t smem = integrate_smem_bytes<Real>(NGAS);                                                  \
+    const size_t smem = SmemLayout<Real, NGAS>::bytes;                                                     \
     auto kern = ufair_integrate_kernel<Real, NGAS, AMODE>;                                                 \
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);    \
     if (e != cudaSuccess) return e;                                                                        \
-    const unsigned grid = (unsigned)((a.n_member + kBlock - 1) / kBlock);                                  \
-    kern<<<grid, kBlock, smem, stream>>>(a);                                                               \
+    const unsigned grid = (unsigned)((a.n_member + kMemb - 1) / kMemb);                                    \
+    kern<<<grid, NGAS * kMemb, smem, stream>>>(a);                                                         \
     return cudaGetLastError();                                                                             \
   }
 

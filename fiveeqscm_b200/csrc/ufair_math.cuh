@@ -109,7 +109,9 @@ template <> struct Math<double> {
     }
     double m = __hiloint2double(mh, lo);
     double f = m - 1.0;
-    double s = f * rcp(m + 1.0);
+    double d = m + 1.0, rc = rcp(d);
+    double s = f * rc;
+    s = fma(fma(-s, d, f), rc, s);  // one correction step: s = f/d to ~0.5 ulp (2 s is the leading term)
     double w = s * s;
     double L = 0x1.2b584aae78a57p-3;
     L = fma(L, w, 0x1.39fe606542ddep-3);

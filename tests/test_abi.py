@@ -46,7 +46,7 @@ def test_binding_covers_every_declared_symbol():
 def test_abi_version_and_struct_size(built):
     L = _abi.lib()
     assert L.ufair_abi_version() == _abi.ABI_VERSION
-    assert L.ufair_block_members() == 128
+    assert L.ufair_block_members() % 32 == 0 and L.ufair_block_members() > 0
     # a descriptor with the wrong struct_size is rejected before anything touches the device
     d = _abi.UfairDesc(n_gas=1, n_t=1, n_member=1, ld_member=2)
     d.struct_size = 8

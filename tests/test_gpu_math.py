@@ -45,7 +45,7 @@ def test_decay_f64(rng):
 
 
 def test_exp_f64(rng):
-    x = np.concatenate([rng.uniform(-30, 30, 300_000), rng.uniform(-1e-3, 1e-3, 1000), [0.0, -700.0, 700.0]])
+    x = np.concatenate([rng.uniform(-30, 30, 300_000), rng.uniform(-1e-3, 1e-3, 1000), [0.0, -690.0, 690.0]])
     assert _ulps(_probe("exp", x), np.exp(_ld(x))) <= 2.0
 
 
