@@ -289,6 +289,8 @@ class DevicePlan:
             buf = new(G, n_t, ld); d.out_RF = buf.data_ptr(); res.RF = buf[..., :M]
         if "T" in outputs:
             buf = new(n_t, ld); d.out_T = buf.data_ptr(); res.T = buf[..., :M]
+        elif stats is not None:  # the moments pass reads the T rows: scratch the caller never sees
+            self._t_scratch = new(n_t, ld); d.out_T = self._t_scratch.data_ptr()
         if "alpha" in outputs:
             buf = new(G, n_t, ld); d.out_alpha = buf.data_ptr(); res.alpha = buf[..., :M]
         if return_state:

@@ -1,6 +1,7 @@
 // ufair_abi.cu -- extern "C" entry points of libufair.so (include/ufair.h): argument checking,
 // dispatch to the fused integrator instantiations, and the small kernels either side of it
 // (statistics reset/finalise, g_1/g_0, k_q, the reference's one-box pulse, peak microbenchmarks).
+#include <cuda.h>
 #include <cuda_runtime.h>
 #include <math.h>
 #include <stdarg.h>
@@ -64,6 +65,7 @@ int validate_desc(const ufair_desc* d, size_t elem) {
   if (d->stats) {
     if (d->hist_bins < 1 || d->hist_copies < 1 || !(d->hist_hi > d->hist_lo) || !d->hist_private || !d->moments_private)
       return set_error(UFAIR_ERR_ARG, "stats requested but histogram spec/buffers incomplete");
+    if (!d->out_T) return set_error(UFAIR_ERR_ARG, "stats need out_T (the moments pass reads the T rows)");
     if (d->hist_t0 < 0 || d->hist_rows < d->hist_t0 + d->n_t)
       return set_error(UFAIR_ERR_ARG, "hist_rows %d < hist_t0 %d + n_t %d", d->hist_rows, d->hist_t0, d->n_t);
   }
@@ -106,16 +108,118 @@ template <typename Real> static KArgs<Real> make_args(const ufair_desc* d) {
   a.hist_lo = (Real)d->hist_lo;
   a.hist_invw = d->stats ? (Real)((Real)d->hist_bins / ((Real)d->hist_hi - (Real)d->hist_lo)) : (Real)0;
   a.hist = d->hist_private;
-  a.mom = d->moments_private;
   return a;
 }
 
-template <typename Real, int NGAS> static cudaError_t dispatch_mode(const KArgs<Real>& a, int mode, cudaStream_t s) {
+// ---- tensor maps for the per-warp TMA pipelines (cuTensorMapEncodeTiled via the runtime's driver
+// entry point, so libufair.so does not link libcuda) ---------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn encode_tiled() {
+  static EncodeTiledFn fn = [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess ||
+        q != cudaDriverEntryPointSuccess)
+      p = nullptr;
+    return (EncodeTiledFn)p;
+  }();
+  return fn;
+}
+
+// emissions [n_gas][n_t][ld] -> rank-3 map, box = MW members x kTT steps x n_gas gases;
+// f_ext [n_t][ld] -> rank-2 map, box = MW x kTT.  Out-of-range parts of a box are zero-filled.
+template <typename Real> static int make_tensor_maps(const ufair_desc* d, CUtensorMap* tmE, CUtensorMap* tmF) {
+  memset(tmE, 0, sizeof(*tmE));
+  memset(tmF, 0, sizeof(*tmF));
+  const bool e_member = d->e_mode == UFAIR_E_MEMBER, f_member = d->fext_mode == UFAIR_FEXT_MEMBER;
+  if (!e_member && !f_member) return UFAIR_OK;
+  EncodeTiledFn enc = encode_tiled();
+  if (!enc) return set_error(UFAIR_ERR_CUDA, "cuTensorMapEncodeTiled is not available from this driver");
+  const CUtensorMapDataType dt = sizeof(Real) == 8 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT64 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32;
+  const cuuint32_t mw = (cuuint32_t)members_per_warp(sizeof(Real), d->n_gas);
+  const cuuint64_t row = (cuuint64_t)d->ld_member * sizeof(Real);
+  const cuuint32_t ones[3] = {1, 1, 1};
+  if (e_member) {
+    const cuuint64_t dims[3] = {(cuuint64_t)d->ld_member, (cuuint64_t)d->n_t, (cuuint64_t)d->n_gas};
+    const cuuint64_t strides[2] = {row, row * (cuuint64_t)d->n_t};
+    const cuuint32_t box[3] = {mw, (cuuint32_t)kTT, (cuuint32_t)d->n_gas};
+    CUresult r = enc(tmE, dt, 3, const_cast<void*>(d->emissions), dims, strides, box, ones, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                     CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return set_error(UFAIR_ERR_CUDA, "cuTensorMapEncodeTiled(emissions) failed: %d", (int)r);
+  }
+  if (f_member) {
+    const cuuint64_t dims[2] = {(cuuint64_t)d->ld_member, (cuuint64_t)d->n_t};
+    const cuuint64_t strides[1] = {row};
+    const cuuint32_t box[2] = {mw, (cuuint32_t)kTT};
+    CUresult r = enc(tmF, dt, 2, const_cast<void*>(d->f_ext), dims, strides, box, ones, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                     CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return set_error(UFAIR_ERR_CUDA, "cuTensorMapEncodeTiled(f_ext) failed: %d", (int)r);
+  }
+  return UFAIR_OK;
+}
+
+template <typename Real, int NGAS>
+static cudaError_t dispatch_mode(const KArgs<Real>& a, const CUtensorMap& tmE, const CUtensorMap& tmF, int mode,
+                                 cudaStream_t s) {
   switch (mode) {
-    case UFAIR_ALPHA_EXP: return launch_integrate<Real, NGAS, UFAIR_ALPHA_EXP>(a, s);
-    case UFAIR_ALPHA_SINH: return launch_integrate<Real, NGAS, UFAIR_ALPHA_SINH>(a, s);
-    case UFAIR_ALPHA_NEWTON: return launch_integrate<Real, NGAS, UFAIR_ALPHA_NEWTON>(a, s);
-    default: return launch_integrate<Real, NGAS, UFAIR_ALPHA_ONE>(a, s);
+    case UFAIR_ALPHA_EXP: return launch_integrate<Real, NGAS, UFAIR_ALPHA_EXP>(a, tmE, tmF, s);
+    case UFAIR_ALPHA_SINH: return launch_integrate<Real, NGAS, UFAIR_ALPHA_SINH>(a, tmE, tmF, s);
+    case UFAIR_ALPHA_NEWTON: return launch_integrate<Real, NGAS, UFAIR_ALPHA_NEWTON>(a, tmE, tmF, s);
+    default: return launch_integrate<Real, NGAS, UFAIR_ALPHA_ONE>(a, tmE, tmF, s);
+  }
+}
+
+// ---- moments of T: second pass over the T rows the integrator just wrote ---------------------------
+// CTA (c, t) folds member slice c of row t in a fixed order (strided per-thread partials, shuffle
+// tree, warps in order) and merges it into moments_private[c][hist_t0 + t]: no atomics, deterministic.
+template <typename Real>
+__global__ void __launch_bounds__(256)
+    moments_pass_kernel(const Real* __restrict__ T, long long ld, long long n_member, int t0_row, int rows, double* mp) {
+  const int c = blockIdx.x, copies = gridDim.x, t = blockIdx.y;
+  const long long lo = n_member * c / copies, hi = n_member * (c + 1) / copies;
+  const Real* row = T + (long long)t * ld;
+  double sm = 0.0, ss = 0.0, mn = INFINITY, mx = -INFINITY;
+  for (long long m = lo + threadIdx.x; m < hi; m += blockDim.x) {
+    const double v = (double)__ldcs(row + m);
+    sm += v;
+    ss = fma(v, v, ss);
+    mn = fmin(mn, v);
+    mx = fmax(mx, v);
+  }
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) {
+    sm += __shfl_xor_sync(0xffffffffu, sm, off);
+    ss += __shfl_xor_sync(0xffffffffu, ss, off);
+    mn = fmin(mn, __shfl_xor_sync(0xffffffffu, mn, off));
+    mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, off));
+  }
+  __shared__ double red[8][4];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  if (lane == 0) {
+    red[w][0] = sm;
+    red[w][1] = ss;
+    red[w][2] = mn;
+    red[w][3] = mx;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double* o = mp + ((size_t)c * rows + t0_row + t) * UFAIR_MOM_COUNT;
+    sm = o[UFAIR_MOM_SUM];
+    ss = o[UFAIR_MOM_SUMSQ];
+    mn = o[UFAIR_MOM_MIN];
+    mx = o[UFAIR_MOM_MAX];
+    for (int k = 0; k < (int)(blockDim.x >> 5); ++k) {
+      sm += red[k][0];
+      ss += red[k][1];
+      mn = fmin(mn, red[k][2]);
+      mx = fmax(mx, red[k][3]);
+    }
+    o[UFAIR_MOM_SUM] = sm;
+    o[UFAIR_MOM_SUMSQ] = ss;
+    o[UFAIR_MOM_MIN] = mn;
+    o[UFAIR_MOM_MAX] = mx;
   }
 }
 
@@ -124,14 +228,23 @@ template <typename Real> int run_device(const ufair_desc* d, cudaStream_t stream
   if (rc != UFAIR_OK) return rc;
   if (d->n_member == 0 || d->n_t == 0) return UFAIR_OK;
   KArgs<Real> a = make_args<Real>(d);
+  CUtensorMap tmE, tmF;
+  rc = make_tensor_maps<Real>(d, &tmE, &tmF);
+  if (rc != UFAIR_OK) return rc;
   cudaError_t e;
   switch (d->n_gas) {
-    case 1: e = dispatch_mode<Real, 1>(a, d->alpha_mode, stream); break;
-    case 2: e = dispatch_mode<Real, 2>(a, d->alpha_mode, stream); break;
-    case 3: e = dispatch_mode<Real, 3>(a, d->alpha_mode, stream); break;
-    default: e = dispatch_mode<Real, 4>(a, d->alpha_mode, stream); break;
+    case 1: e = dispatch_mode<Real, 1>(a, tmE, tmF, d->alpha_mode, stream); break;
+    case 2: e = dispatch_mode<Real, 2>(a, tmE, tmF, d->alpha_mode, stream); break;
+    case 3: e = dispatch_mode<Real, 3>(a, tmE, tmF, d->alpha_mode, stream); break;
+    default: e = dispatch_mode<Real, 4>(a, tmE, tmF, d->alpha_mode, stream); break;
   }
   if (e != cudaSuccess) return cuda_error(e, "ufair_integrate_kernel launch");
+  if (d->stats) {
+    moments_pass_kernel<Real><<<dim3((unsigned)d->hist_copies, (unsigned)d->n_t), 256, 0, stream>>>(
+        (const Real*)d->out_T, d->ld_member, d->n_member, d->hist_t0, d->hist_rows, d->moments_private);
+    e = cudaGetLastError();
+    if (e != cudaSuccess) return cuda_error(e, "moments_pass_kernel launch");
+  }
   return UFAIR_OK;
 }
 template int run_device<double>(const ufair_desc*, cudaStream_t);
@@ -145,8 +258,8 @@ __global__ void stats_reset_kernel(unsigned int* hist, size_t n_hist, double* mo
     double* r = mom + i * UFAIR_MOM_COUNT;
     r[UFAIR_MOM_SUM] = 0.0;
     r[UFAIR_MOM_SUMSQ] = 0.0;
-    reinterpret_cast<unsigned long long*>(r)[UFAIR_MOM_MIN] = 0xffffffffffffffffull;
-    reinterpret_cast<unsigned long long*>(r)[UFAIR_MOM_MAX] = 0ull;
+    r[UFAIR_MOM_MIN] = INFINITY;
+    r[UFAIR_MOM_MAX] = -INFINITY;
   }
 }
 
@@ -160,22 +273,19 @@ __global__ void stats_finalize_kernel(const unsigned int* hp, const double* mp, 
     hist[i] = s;
   }
   for (size_t r = i0; r < (size_t)rows; r += stride) {
-    double sm = 0.0, ss = 0.0;
-    unsigned long long mn = 0xffffffffffffffffull, mx = 0ull;
-    for (int c = 0; c < copies; ++c) {  // fixed order: deterministic given the private copies
+    double sm = 0.0, ss = 0.0, mn = INFINITY, mx = -INFINITY;
+    for (int c = 0; c < copies; ++c) {  // fixed order: deterministic
       const double* p = mp + ((size_t)c * rows + r) * UFAIR_MOM_COUNT;
       sm += p[UFAIR_MOM_SUM];
       ss += p[UFAIR_MOM_SUMSQ];
-      const unsigned long long a = reinterpret_cast<const unsigned long long*>(p)[UFAIR_MOM_MIN];
-      const unsigned long long b = reinterpret_cast<const unsigned long long*>(p)[UFAIR_MOM_MAX];
-      mn = a < mn ? a : mn;
-      mx = b > mx ? b : mx;
+      mn = fmin(mn, p[UFAIR_MOM_MIN]);
+      mx = fmax(mx, p[UFAIR_MOM_MAX]);
     }
     double* o = mom + r * UFAIR_MOM_COUNT;
     o[UFAIR_MOM_SUM] = sm;
     o[UFAIR_MOM_SUMSQ] = ss;
-    o[UFAIR_MOM_MIN] = dec_ordered(mn);
-    o[UFAIR_MOM_MAX] = dec_ordered(mx);
+    o[UFAIR_MOM_MIN] = mn;
+    o[UFAIR_MOM_MAX] = mx;
   }
 }
 
@@ -302,7 +412,7 @@ extern "C" {
 
 int ufair_abi_version(void) { return UFAIR_ABI_VERSION; }
 const char* ufair_last_error(void) { return g_err; }
-int64_t ufair_block_members(void) { return kMemb; }
+int64_t ufair_block_members(void) { return kWarps * 32; }
 
 int ufair_run_f64(const ufair_desc* d, void* stream) { return run_device<double>(d, (cudaStream_t)stream); }
 int ufair_run_f32(const ufair_desc* d, void* stream) { return run_device<float>(d, (cudaStream_t)stream); }

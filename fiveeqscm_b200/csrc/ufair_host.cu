@@ -96,7 +96,7 @@ static int run_chunks(ufair_workspace* ws, const ufair_desc* h, const ufair_desc
                          {B_ESC, (size_t)G, esc_on},
                          {B_OC, (size_t)G * n_t, (h->out_mask & UFAIR_OUT_C) != 0},
                          {B_ORF, (size_t)G * n_t, (h->out_mask & UFAIR_OUT_RF) != 0},
-                         {B_OT, (size_t)n_t, (h->out_mask & UFAIR_OUT_T) != 0},
+                         {B_OT, (size_t)n_t, (h->out_mask & UFAIR_OUT_T) != 0 || h->stats != 0},  // moments pass reads T
                          {B_OA, (size_t)G * n_t, (h->out_mask & UFAIR_OUT_ALPHA) != 0},
                          {B_SOUT, srows, h->state_out != nullptr}};
     if (S.used) {  // staging of chunk c-2: inputs consumed by its kernel, outputs copied out

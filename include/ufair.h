@@ -138,17 +138,20 @@ typedef struct ufair_desc {
   /* ---- ensemble statistics (stats == 1) ----
    * bin(T) = clamp(floor((T - hist_lo) * (hist_bins / (hist_hi - hist_lo))), 0, hist_bins-1),
    * evaluated in the run's precision; NaN is not counted.
-   * The kernel adds into `hist_copies` private copies (block b -> copy b % hist_copies)
-   * which the caller zeroes once and may keep accumulating over several calls
-   * (member chunks); ufair_stats_finalize() folds them. */
+   * The integrator adds into `hist_copies` private histogram copies (warp w -> copy
+   * w % hist_copies); the moments (sum, sum of squares, min, max of T over members) come from a
+   * second pass over the T rows the integrator wrote, so out_T must be non-NULL when stats == 1
+   * (whether or not UFAIR_OUT_T is set).  ufair_stats_reset() initialises the private buffers
+   * once; they may keep accumulating over several calls (member chunks);
+   * ufair_stats_finalize() folds them. */
   int32_t hist_bins;
   int32_t hist_copies;
   double hist_lo, hist_hi;
   int32_t hist_t0;          /* row offset: step t of this call lands in row hist_t0 + t */
   int32_t hist_rows;        /* rows allocated per copy (>= hist_t0 + n_t) */
   uint32_t* hist_private;   /* [hist_copies][hist_rows][hist_bins] */
-  double* moments_private;  /* [hist_copies][hist_rows][UFAIR_MOM_COUNT]; min/max rows hold
-                               order-preserving uint64 encodings until finalize */
+  double* moments_private;  /* [hist_copies][hist_rows][UFAIR_MOM_COUNT]: member slice c of every
+                               row is folded into copy c, in a fixed order (deterministic) */
 } ufair_desc;
 
 /* ---- version / errors ---- */

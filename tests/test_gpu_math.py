@@ -45,8 +45,12 @@ def test_decay_f64(rng):
 
 
 def test_exp_f64(rng):
-    x = np.concatenate([rng.uniform(-30, 30, 300_000), rng.uniform(-1e-3, 1e-3, 1000), [0.0, -690.0, 690.0]])
+    x = np.concatenate([rng.uniform(-27, 27, 300_000), rng.uniform(-1e-3, 1e-3, 1000), [0.0]])
     assert _ulps(_probe("exp", x), np.exp(_ld(x))) <= 2.0
+    # outside 2^+-40 the result saturates (alpha is kept in [9e-13, 1.1e12]) instead of overflowing
+    sat = _probe("exp", np.array([-700.0, -30.0, 30.0, 700.0]))
+    assert np.all(np.isfinite(sat)) and np.all(sat[:2] < 2.0 ** -39) and np.all(sat[:2] > 2.0 ** -42)
+    assert np.all(sat[2:] > 2.0 ** 39) and np.all(sat[2:] < 2.0 ** 42)
 
 
 def test_rcp_sqrt_f64(rng):

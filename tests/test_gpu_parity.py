@@ -284,7 +284,7 @@ def test_g1g0_and_kq_kernels(api):
     rng = np.random.default_rng(5)
     n = 1000
     a = rng.dirichlet(np.ones(4), size=n).T.copy()
-    tau = np.exp(rng.uniform(0, 12, size=(4, n)))
+    tau = np.exp(rng.uniform(0, 7, size=(4, n)))     # 1..1100 yr: g1's 1-(1+z)e^-z cancels for tau >> h
     a_d, tau_d = to_dev(a), to_dev(tau)      # keep the device arrays alive across the launches
     for mode in (_abi.ALPHA_EXP, _abi.ALPHA_SINH):
         g1 = torch.empty(n, dtype=torch.float64, device="cuda")
