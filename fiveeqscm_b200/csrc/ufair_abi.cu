@@ -239,14 +239,22 @@ template <typename Real> int run_device(const ufair_desc* d, cudaStream_t stream
     default: e = dispatch_mode<Real, 4>(a, tmE, tmF, d->alpha_mode, stream); break;
   }
   if (e != cudaSuccess) return cuda_error(e, "ufair_integrate_kernel launch");
-  if (d->stats) {
-    moments_pass_kernel<Real><<<dim3((unsigned)d->hist_copies, (unsigned)d->n_t), 256, 0, stream>>>(
-        (const Real*)d->out_T, d->ld_member, d->n_member, d->hist_t0, d->hist_rows, d->moments_private);
-    e = cudaGetLastError();
-    if (e != cudaSuccess) return cuda_error(e, "moments_pass_kernel launch");
-  }
   return UFAIR_OK;
 }
+
+template <typename Real> int run_moments(const ufair_desc* d, cudaStream_t stream) {
+  int rc = validate_desc(d, sizeof(Real));
+  if (rc != UFAIR_OK) return rc;
+  if (!d->stats) return set_error(UFAIR_ERR_ARG, "ufair_stats_moments: descriptor has stats == 0");
+  if (d->n_member == 0 || d->n_t == 0) return UFAIR_OK;
+  moments_pass_kernel<Real><<<dim3((unsigned)d->hist_copies, (unsigned)d->n_t), 256, 0, stream>>>(
+      (const Real*)d->out_T, d->ld_member, d->n_member, d->hist_t0, d->hist_rows, d->moments_private);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return cuda_error(e, "moments_pass_kernel launch");
+  return UFAIR_OK;
+}
+template int run_moments<double>(const ufair_desc*, cudaStream_t);
+template int run_moments<float>(const ufair_desc*, cudaStream_t);
 template int run_device<double>(const ufair_desc*, cudaStream_t);
 template int run_device<float>(const ufair_desc*, cudaStream_t);
 
@@ -416,6 +424,9 @@ int64_t ufair_block_members(void) { return kWarps * 32; }
 
 int ufair_run_f64(const ufair_desc* d, void* stream) { return run_device<double>(d, (cudaStream_t)stream); }
 int ufair_run_f32(const ufair_desc* d, void* stream) { return run_device<float>(d, (cudaStream_t)stream); }
+
+int ufair_stats_moments_f64(const ufair_desc* d, void* stream) { return run_moments<double>(d, (cudaStream_t)stream); }
+int ufair_stats_moments_f32(const ufair_desc* d, void* stream) { return run_moments<float>(d, (cudaStream_t)stream); }
 
 int ufair_stats_reset(const ufair_desc* d, void* stream) {
   int rc = check_stats_desc(d);

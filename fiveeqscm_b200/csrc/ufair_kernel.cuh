@@ -1,25 +1,31 @@
 // ufair_kernel.cuh -- the fused Universal-FaIR time-stepping kernel (sm_100a).
 //
-// Work decomposition (v5): one LANE = one (member, gas) pair; one WARP = MW consecutive members x
-// all NGAS gases (f64: MW = 32, 16, 10, 8 for 1..4 gases; lanes beyond NGAS*MW idle).  The NGAS
-// lanes of a member exchange their radiative forcings with warp shuffles, so a warp never waits
-// for another warp: there is NO block-level synchronisation anywhere in the kernel.  Each warp
-// runs its own TMA pipeline (its own shared-memory ring and mbarriers).
-//   Every lane keeps its gas's four pools, cumulative emissions and (redundantly, bit-identically
-//   in the NGAS lanes of a member) the two thermal boxes in REGISTERS across the serial time loop;
-//   its 23 derived per-member constants sit in shared memory ([param][lane], conflict-free
-//   LDS.64 addressed as base + immediate) so that the registers they would pin are free for
-//   instruction-level parallelism across the four independent pool exponentials.
-//   Why: the loop is a chain of dependent DFMAs (Horner polynomials) and is bound by the warp
+// Work decomposition.  A WARP owns MW consecutive ensemble members and runs its own TMA pipeline
+// (its own shared-memory ring and mbarriers); warps never wait for each other -- there is NO
+// block-level synchronisation anywhere in the kernel.  Inside the warp a lane integrates either
+//   GPL = 1    : ONE gas of one member    (default; MW = 32, 16, 10, 8 members per warp for 1..4
+//                                          gases; the NGAS lanes of a member add up their forcings
+//                                          with warp shuffles), or
+//   GPL = NGAS : ALL gases of one member  (MW = 32; build with -DUFAIR_GPL_ALL=1).
+//   Pools, cumulative emissions and the two thermal boxes stay in REGISTERS across the serial time
+//   loop; most derived per-member constants sit in shared memory ([param][lane], conflict-free
+//   LDS.64 at base + immediate) so the registers they would pin are free for instruction-level
+//   parallelism across the independent pool / gas exponentials.
+//   Why: the loop is chains of dependent DFMAs (Horner polynomials); it is bound by the warp
 //   schedulers' issue rate and dependent-issue latency, not by HBM.  ncu history (profiles/):
-//     v1 thread per member, 255 regs, 2 warps/SMSP:  FP64 pipe 35 % busy, stall_wait 3.3 / issue
+//     v1 thread per member, everything in regs (255), 2 warps/SMSP: FP64 pipe 35 %, IPC 0.37
 //     v2 warp per gas + named barrier, 96 regs:      FP64 42 %, 61 % of issue slots non-FP64
 //     v3 + constants in c[3], params in smem:        FP64 52 %, 19 % of samples in barrier stalls
-//     v4 lanes = (member, gas), shuffles, no barrier: issue slots 69 % busy, 413 instr / warp-step
-//        of which 161 FP64; ~40 / step were per-row TMA issue (R2UR + UBLKCP, 12 rows per tile)
-//     v5 (this file): one 3-D tensor-map TMA per warp-tile, unrolled tile body, running pointers.
-//   The loop body is alpha_val -> step_conc -> step_forc -> (shuffle) -> step_temp, the names the
-//   reference reserves in .coveragerc:12-19; `oxfair` is ONE launch.
+//     v4 lanes = (member, gas), shuffles, no barrier: IPC 0.69, 413 instr / 10-member warp-step,
+//        ~40 of them per-row TMA issue (R2UR + UBLKCP, 12 rows per tile)
+//     v5 one 3-D tensor-map TMA per warp-tile, pinned smem addresses, running pointers: 335 instr
+//        per 10-member warp-step, IPC 0.69 at 5 warps/SMSP -> 38.7 ms (41.8 with statistics)
+//     v6 = GPL_ALL: a lane integrates all gases of its member again, now with smem constants (no
+//        redundant thermal step, no shuffles, no idle lanes: 27 instr per member-step instead of
+//        33.5) -- but 168 regs leave 3 warps/SMSP and IPC drops to 0.45: 47.8 ms.  Thread-level
+//        parallelism beats instruction count here, so GPL = 1 stays the default.
+//   The loop body is alpha_val -> step_conc -> step_forc -> step_temp, the names the reference
+//   reserves in .coveragerc:12-19; `oxfair` is ONE launch.
 //
 // Memory system
 //   * per-member emissions [gas][t][member] are streamed into the warp's shared-memory ring one
@@ -28,11 +34,10 @@
 //     MW members x TT steps x NGAS gases; out-of-range rows/columns are zero-filled by the
 //     hardware, which is what makes ragged tails free), double-buffered on two mbarriers per warp.
 //     Per-member external forcing rides the same way through a 2-D map.
-//   * C / RF / T are written straight from registers with streaming (st.global.cs) stores; a warp
-//     store covers NGAS contiguous MW-member runs, adjacent warps write adjacent runs -- nothing is
-//     re-read.
-//   * optional statistics: the gas-0 lanes add their member's T to the privatised per-step
-//     histogram (RED.ADD.U32) as they go; moments come from a second, HBM-speed pass over the T
+//   * C / RF / T are written straight from registers with streaming (st.global.cs) stores, one
+//     aligned 256-byte run per warp and row -- nothing is re-read.
+//   * optional statistics: the lane owning a member adds its T to the privatised per-step
+//     histogram (RED.ADD.U32) as it goes; moments come from a second, HBM-speed pass over the T
 //     rows (ufair_abi.cu), which is cheaper than in-loop cross-lane reductions and deterministic.
 #pragma once
 #include <cuda.h>
@@ -42,17 +47,20 @@
 #include "../../include/ufair.h"
 #include "ufair_math.cuh"
 
+#ifndef UFAIR_GPL_ALL
+#define UFAIR_GPL_ALL 0  // 1: a lane integrates all gases of its member; 0: one gas per lane (measured faster)
+#endif
 #ifndef UFAIR_WARPS
 #define UFAIR_WARPS 4  // warps per CTA (a CTA is only a launch / shared-memory grouping)
 #endif
 #ifndef UFAIR_MINB_F64
-#define UFAIR_MINB_F64 5  // resident CTAs per SM the register allocator must allow
+#define UFAIR_MINB_F64 (UFAIR_GPL_ALL ? 3 : 5)  // resident CTAs per SM the register allocator must allow
 #endif
 #ifndef UFAIR_MINB_F32
-#define UFAIR_MINB_F32 8
+#define UFAIR_MINB_F32 (UFAIR_GPL_ALL ? 4 : 8)
 #endif
 #ifndef UFAIR_TT
-#define UFAIR_TT 4  // time steps per shared-memory tile
+#define UFAIR_TT 8  // time steps per shared-memory tile (8 measured ~2 % faster than 4)
 #endif
 
 namespace ufair {
@@ -61,10 +69,12 @@ constexpr int kWarps = UFAIR_WARPS;
 constexpr int kTT = UFAIR_TT;
 constexpr int kStages = 2;  // tile ring depth
 
+constexpr int gases_per_lane(int n_gas) { return UFAIR_GPL_ALL ? n_gas : 1; }
 // members per warp: rows of MW elements must be a multiple of 16 bytes for the TMA box
 constexpr int members_per_warp(int elem_size, int n_gas) {
-  const int q = 16 / elem_size;  // elements per 16 bytes
-  return (32 / n_gas) / q * q;
+  const int q = 16 / elem_size;                          // elements per 16 bytes
+  const int groups = n_gas / gases_per_lane(n_gas);      // lanes per member
+  return (32 / groups) / q * q;
 }
 
 template <typename Real> struct KArgs {
@@ -145,50 +155,48 @@ __device__ __forceinline__ void pin(uint32_t& x) { asm volatile("" : "+r"(x)); }
 
 template <typename Real> __device__ __forceinline__ void st_stream(Real* p, Real v) { __stcs(p, v); }
 
-// per-lane derived constants held in shared memory, [param][lane]
+// per-lane derived constants.  Rows G_* exist once per gas the lane integrates; the five `hot` ones
+// (needed first in a step, on the critical path into alpha) live in registers when a lane carries
+// several gases and in shared memory otherwise.  T_* rows exist once per lane.
 enum {
-  P_KA0 = 0,   // c a_i tau_i: equilibrium pool per unit (E alpha)
-  P_K0 = 4,    // dt / tau_i   (ALPHA_ONE: m_i = 1 - exp(-dt/tau_i))
-  P_RHO0 = 8,  // u = rho0 + rhoU Gcum + wR sumR + rhoT T   (= iIRF/g1 [+ ln g0])
-  P_RHOU,
-  P_WR,
-  P_RHOT,
-  P_UMAX,
-  P_C0,
-  P_INVC0,
-  P_SQRTC0,
-  P_F1,
-  P_F2,
-  P_F3,
-  P_QM0,  // q_j (1 - exp(-dt/d_j))
-  P_QM1,
-  P_DEC0,  // exp(-dt/d_j)
-  P_DEC1,
-  P_X0,  // SINH: g0;  NEWTON: g1
-  P_X1,  // NEWTON: ln g0
-  P_X2,  // NEWTON: 1/c
-  P_COUNT
+  G_KA0 = 0,  // c a_i tau_i: equilibrium pool per unit (E alpha)
+  G_K0 = 4,   // dt / tau_i   (ALPHA_ONE: m_i = 1 - exp(-dt/tau_i))
+  G_C0 = 8,
+  G_INVC0,
+  G_SQRTC0,
+  G_F1,
+  G_F2,
+  G_F3,
+  G_COLD  // = 14
 };
+enum { H_RHO0 = 0, H_RHOU, H_WR, H_RHOT, H_UMAX, H_COUNT };  // u = rho0 + rhoU Gcum + wR sumR + rhoT T
+enum { T_QM0 = 0, T_QM1, T_DEC0, T_DEC1, T_COUNT };          // q_j (1 - e^{-dt/d_j}),  e^{-dt/d_j}
 
-// EXP / ONE need none of the P_X* rows, SINH one, NEWTON three
-constexpr int par_count(int amode) {
-  return amode == UFAIR_ALPHA_NEWTON ? P_COUNT : (amode == UFAIR_ALPHA_SINH ? P_X0 + 1 : P_X0);
-}
+constexpr int extra_rows(int amode) { return amode == UFAIR_ALPHA_NEWTON ? 3 : (amode == UFAIR_ALPHA_SINH ? 1 : 0); }
 constexpr size_t round128(size_t b) { return (b + 127) / 128 * 128; }
 
 // per-WARP shared memory, in bytes (every piece 128-byte aligned: tensor-map TMA destinations)
 template <typename Real, int NGAS, int AMODE> struct WarpSmem {
+  static constexpr int GPL = gases_per_lane(NGAS);
+  static constexpr bool HOT_SMEM = (GPL == 1);
   static constexpr int MW = members_per_warp(sizeof(Real), NGAS);
+  static constexpr int G_HOT = G_COLD;                            // first hot row (if in smem)
+  static constexpr int G_X0 = G_COLD + (HOT_SMEM ? H_COUNT : 0);  // SINH: g0; NEWTON: g1, ln g0, 1/c
+  static constexpr int PG = G_X0 + extra_rows(AMODE);             // rows per gas
+  static constexpr int ROWS = GPL * PG + T_COUNT;
   static constexpr uint32_t e_box = (uint32_t)(NGAS * kTT * MW * sizeof(Real));  // bytes one E box delivers
   static constexpr uint32_t f_box = (uint32_t)(kTT * MW * sizeof(Real));         // bytes one f_ext box delivers
   static constexpr uint32_t e_stage = (uint32_t)round128(e_box);
   static constexpr uint32_t f_stage = (uint32_t)round128(f_box);
   static constexpr uint32_t off_e = 0;
   static constexpr uint32_t off_f = off_e + kStages * e_stage;
-  static constexpr uint32_t off_par = off_f + kStages * f_stage;
-  static constexpr uint32_t off_bar = off_par + (uint32_t)round128(par_count(AMODE) * 32 * sizeof(Real));
-  static constexpr uint32_t bytes = off_bar + 128;
-  static constexpr size_t bytes_per_cta = (size_t)bytes * kWarps;
+  static constexpr uint32_t par_bytes = (uint32_t)round128(ROWS * 32 * sizeof(Real));
+  // the f_ext ring exists only when external forcing is per member (decided at launch)
+  static __host__ __device__ constexpr uint32_t off_par(bool fx_member) {
+    return off_f + (fx_member ? kStages * f_stage : 0u);
+  }
+  static __host__ __device__ constexpr uint32_t off_bar(bool fx_member) { return off_par(fx_member) + par_bytes; }
+  static __host__ __device__ constexpr uint32_t bytes(bool fx_member) { return off_bar(fx_member) + 128u; }
 };
 
 constexpr int min_blocks(int elem_size) { return elem_size == 8 ? UFAIR_MINB_F64 : UFAIR_MINB_F32; }
@@ -200,18 +208,23 @@ __global__ void __launch_bounds__(kWarps * 32, min_blocks(sizeof(Real)))
                            const __grid_constant__ CUtensorMap tmF) {
   using M = Math<Real>;
   using WS = WarpSmem<Real, NGAS, AMODE>;
-  constexpr int MW = WS::MW;
-  constexpr int NACT = MW * NGAS;  // working lanes
+  constexpr int GPL = WS::GPL;           // gases this lane integrates
+  constexpr int GROUPS = NGAS / GPL;     // lanes per member
+  constexpr int MW = WS::MW;             // members per warp
+  constexpr int NACT = MW * GROUPS;      // working lanes
+  constexpr bool HOT_SMEM = WS::HOT_SMEM;
   constexpr unsigned FULL = 0xffffffffu;
   constexpr uint32_t ES = sizeof(Real);
+  constexpr uint32_t GROW = (uint32_t)(kTT * MW) * ES;  // bytes between two gases inside an E stage
   extern __shared__ __align__(128) unsigned char smem_raw[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const long long wg = (long long)blockIdx.x * kWarps + warp;  // global warp index
   const long long m0 = wg * MW;                                // first member of this warp
   if (m0 >= a.n_member) return;  // whole warp: nothing to do (no CTA-wide sync exists)
 
-  const int g = min(lane / MW, NGAS - 1);    // this lane's gas     (spare lanes shadow the last pair)
-  const int i = min(lane - g * MW, MW - 1);  // this lane's member inside the warp
+  const int grp = min(lane / MW, GROUPS - 1);  // spare lanes shadow the last group
+  const int i = min(lane - grp * MW, MW - 1);  // this lane's member inside the warp
+  const int g0 = grp * GPL;                    // first gas of this lane
   const long long m_raw = m0 + i;
   const bool active = (lane < NACT) && (m_raw < a.n_member);
   const long long m = min(m_raw, a.n_member - 1);
@@ -222,16 +235,18 @@ __global__ void __launch_bounds__(kWarps * 32, min_blocks(sizeof(Real)))
   const bool fx_scen = (a.fext_mode == UFAIR_FEXT_SCENARIO);
   const bool use_tma = EMEM || fx_member;
 
-  const uint32_t wbase = smem_u32(smem_raw) + (uint32_t)warp * WS::bytes;
-  uint32_t e_addr = wbase + WS::off_e + (uint32_t)(g * kTT * MW + i) * ES;  // this lane's E element, stage 0, tt 0
+  const uint32_t wbase = smem_u32(smem_raw) + (uint32_t)warp * WS::bytes(fx_member);
+  uint32_t e_addr = wbase + WS::off_e + (uint32_t)(g0 * kTT * MW + i) * ES;  // this lane's E element: stage 0, tt 0
   uint32_t f_addr = wbase + WS::off_f + (uint32_t)i * ES;
-  uint32_t par = wbase + WS::off_par + (uint32_t)lane * ES;                 // this lane's parameter column
-  const uint32_t bar0 = wbase + WS::off_bar;
+  uint32_t par = wbase + WS::off_par(fx_member) + (uint32_t)lane * ES;       // this lane's parameter column
+  const uint32_t bar0 = wbase + WS::off_bar(fx_member);
   pin(e_addr);
   pin(f_addr);
   pin(par);
-#define PAR(k) lds(par + (uint32_t)(k) * 32u * ES, Real())
-#define SETPAR(k, v) sts(par + (uint32_t)(k) * 32u * ES, (Real)(v))
+#define PARG(gl, k) lds(par + (uint32_t)((gl) * WS::PG + (k)) * 32u * ES, Real())
+#define SETG(gl, k, v) sts(par + (uint32_t)((gl) * WS::PG + (k)) * 32u * ES, (Real)(v))
+#define PART(k) lds(par + (uint32_t)(GPL * WS::PG + (k)) * 32u * ES, Real())
+#define SETT(k, v) sts(par + (uint32_t)(GPL * WS::PG + (k)) * 32u * ES, (Real)(v))
 
   const int n_tile = (n_t + kTT - 1) / kTT;
   if (lane == 0 && use_tma) {
@@ -251,8 +266,13 @@ __global__ void __launch_bounds__(kWarps * 32, min_blocks(sizeof(Real)))
   // ---------------- prologue: raw parameters -> derived constants, in double for both precisions
   // (g_1 and g_0 of .coveragerc:15-16 are fused here; in FP32 they would cancel catastrophically
   // for the 10^6-year pool, so the one-off prologue always runs in FP64 and rounds once)
-  Real R0, R1, R2, R3, Gcum, sumR;
-  {
+  Real R[GPL][4], Gcum[GPL], sumR[GPL];
+  Real hot[GPL][H_COUNT];  // used only when !HOT_SMEM (dead otherwise)
+  unsigned mk1[GPL], mk3[GPL];
+  bool need_log[GPL], need_sqrt[GPL];
+#pragma unroll
+  for (int gl = 0; gl < GPL; ++gl) {
+    const int g = g0 + gl;
     const Real* p = a.gp + (long long)g * UFAIR_GP_COUNT * ld + m;
     double av[4], tau[4];
 #pragma unroll
@@ -276,33 +296,42 @@ __global__ void __launch_bounds__(kWarps * 32, min_blocks(sizeof(Real)))
     const double fold = (AMODE == UFAIR_ALPHA_SINH) ? 0.0 : lng0;
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
-      SETPAR(P_KA0 + q, c * av[q] * tau[q]);
-      SETPAR(P_K0 + q, (AMODE == UFAIR_ALPHA_ONE) ? -expm1(-a.dt / tau[q]) : a.dt / tau[q]);
+      SETG(gl, G_KA0 + q, c * av[q] * tau[q]);
+      SETG(gl, G_K0 + q, (AMODE == UFAIR_ALPHA_ONE) ? -expm1(-a.dt / tau[q]) : a.dt / tau[q]);
     }
-    SETPAR(P_RHO0, r0 * inv_g1 + fold);
-    SETPAR(P_RHOU, rU * inv_g1);
-    SETPAR(P_WR, (rA - rU) * inv_g1 * invc);
-    SETPAR(P_RHOT, rT * inv_g1);
-    SETPAR(P_UMAX, a.clamp ? (a.iirf_max * inv_g1 + fold) : (double)INFINITY);
-    SETPAR(P_C0, C0d);
-    SETPAR(P_INVC0, 1.0 / C0d);
-    SETPAR(P_SQRTC0, sqrt(C0d));
-    SETPAR(P_F1, p[UFAIR_GP_F1 * ld]);
-    SETPAR(P_F2, p[UFAIR_GP_F2 * ld]);
-    SETPAR(P_F3, p[UFAIR_GP_F3 * ld]);
-    if (AMODE == UFAIR_ALPHA_SINH) SETPAR(P_X0, 1.0 / sinh(sarg));
+    const double hv[H_COUNT] = {r0 * inv_g1 + fold, rU * inv_g1, (rA - rU) * inv_g1 * invc, rT * inv_g1,
+                                a.clamp ? (a.iirf_max * inv_g1 + fold) : (double)INFINITY};
+#pragma unroll
+    for (int q = 0; q < H_COUNT; ++q) {
+      hot[gl][q] = (Real)hv[q];
+      if (HOT_SMEM) SETG(gl, WS::G_HOT + q, hv[q]);
+    }
+    SETG(gl, G_C0, C0d);
+    SETG(gl, G_INVC0, 1.0 / C0d);
+    SETG(gl, G_SQRTC0, sqrt(C0d));
+    const Real f1v = p[UFAIR_GP_F1 * ld], f3v = p[UFAIR_GP_F3 * ld];
+    SETG(gl, G_F1, f1v);
+    SETG(gl, G_F2, p[UFAIR_GP_F2 * ld]);
+    SETG(gl, G_F3, f3v);
+    if (AMODE == UFAIR_ALPHA_SINH) SETG(gl, WS::G_X0, 1.0 / sinh(sarg));
     if (AMODE == UFAIR_ALPHA_NEWTON) {
-      SETPAR(P_X0, g1);
-      SETPAR(P_X1, lng0);
-      SETPAR(P_X2, invc);
+      SETG(gl, WS::G_X0, g1);
+      SETG(gl, WS::G_X0 + 1, lng0);
+      SETG(gl, WS::G_X0 + 2, invc);
     }
+    // a zero forcing coefficient means a zero term; the log / sqrt is skipped only when no lane of
+    // the warp needs it (voted once, outside the loop; with all gases in one lane this is per gas)
+    need_log[gl] = __any_sync(FULL, f1v != Real(0));
+    need_sqrt[gl] = __any_sync(FULL, f3v != Real(0));
+    mk1[gl] = (f1v != Real(0)) ? 0xffffffffu : 0u;
+    mk3[gl] = (f3v != Real(0)) ? 0xffffffffu : 0u;
+    pin(mk1[gl]);
+    pin(mk3[gl]);
     const Real* si = a.state_in;
-    R0 = si ? si[(long long)(5 * g + 0) * ld + m] : Real(0);
-    R1 = si ? si[(long long)(5 * g + 1) * ld + m] : Real(0);
-    R2 = si ? si[(long long)(5 * g + 2) * ld + m] : Real(0);
-    R3 = si ? si[(long long)(5 * g + 3) * ld + m] : Real(0);
-    Gcum = si ? si[(long long)(5 * g + 4) * ld + m] : Real(0);
-    sumR = (R0 + R1) + (R2 + R3);
+#pragma unroll
+    for (int q = 0; q < 4; ++q) R[gl][q] = si ? si[(long long)(5 * g + q) * ld + m] : Real(0);
+    Gcum[gl] = si ? si[(long long)(5 * g + 4) * ld + m] : Real(0);
+    sumR[gl] = (R[gl][0] + R[gl][1]) + (R[gl][2] + R[gl][3]);
   }
   Real S0, S1, Tprev;
   {
@@ -312,36 +341,28 @@ __global__ void __launch_bounds__(kWarps * 32, min_blocks(sizeof(Real)))
     for (int q = 0; q < 2; ++q) {
       const double qq = tp[(UFAIR_TP_Q1 + q) * ld], d = tp[(UFAIR_TP_D1 + q) * ld];
       const double mj = -expm1(-a.dt / d);
-      SETPAR(P_QM0 + q, qq * mj);
-      SETPAR(P_DEC0 + q, 1.0 - mj);
+      SETT(T_QM0 + q, qq * mj);
+      SETT(T_DEC0 + q, 1.0 - mj);
     }
     S0 = si ? si[(long long)(5 * NGAS + 0) * ld + m] : Real(0);
     S1 = si ? si[(long long)(5 * NGAS + 1) * ld + m] : Real(0);
     Tprev = si ? si[(long long)(5 * NGAS + 2) * ld + m] : Real(0);
   }
   __syncwarp();
-  // a zero forcing coefficient means a zero term; the log / sqrt is skipped only when no lane of
-  // the warp needs it (voted once, outside the loop)
-  const Real f1v = PAR(P_F1), f3v = PAR(P_F3);
-  const bool need_log = __any_sync(FULL, f1v != Real(0));
-  const bool need_sqrt = __any_sync(FULL, f3v != Real(0));
-  unsigned mk1 = (f1v != Real(0)) ? 0xffffffffu : 0u, mk3 = (f3v != Real(0)) ? 0xffffffffu : 0u;
-  pin(mk1);
-  pin(mk3);
 
   const int scen = (a.scen_idx != nullptr) ? a.scen_idx[m] : 0;
-  const Real esc = (!EMEM && a.e_scale) ? a.e_scale[(long long)g * ld + m] : Real(1);
   const Real dt = (Real)a.dt;
   const Real hdt = (Real)(a.h / a.dt);
   const bool t_mid = (a.t_mode == UFAIR_T_MID);
 
-  // output predicates packed in one register; running output pointers
-  const bool do_hist = a.stats && active && (g == 0);
+  // output predicates packed in one register; running output pointers (gas g0; + gl * gstride)
+  const bool owner = active && (g0 == 0);  // the lane that owns the member's T / histogram count
   unsigned wm = (active ? (unsigned)(a.out_mask & (UFAIR_OUT_C | UFAIR_OUT_RF | UFAIR_OUT_ALPHA)) : 0u) |
-                ((active && g == 0 && ((a.out_mask & UFAIR_OUT_T) || a.stats)) ? (unsigned)UFAIR_OUT_T : 0u) |
-                (do_hist ? 16u : 0u);
+                ((owner && ((a.out_mask & UFAIR_OUT_T) || a.stats)) ? (unsigned)UFAIR_OUT_T : 0u) |
+                ((owner && a.stats) ? 16u : 0u);
   pin(wm);
-  const long long o_gas = (long long)g * n_t * ld + m_raw;
+  const long long gstride = (long long)n_t * ld;
+  const long long o_gas = (long long)g0 * gstride + m_raw;
   Real* pC = a.oC + o_gas;
   Real* pRF = a.oRF + o_gas;
   Real* pA = a.oA + o_gas;
@@ -350,101 +371,112 @@ __global__ void __launch_bounds__(kWarps * 32, min_blocks(sizeof(Real)))
   const int bins_m1 = a.hist_bins - 1;
 
   // scenario-mode inputs: register prefetch one step ahead through the read-only path
-  Real e_next = 0, fx_next = 0;
-  const Real* e_scen = a.E + ((long long)g * n_t) * a.n_scen + scen;
+  Real e_next[GPL], esc[GPL], fx_next = 0;
+  const Real* e_scen = a.E + ((long long)g0 * n_t) * a.n_scen + scen;
+  const long long scen_gstride = (long long)n_t * a.n_scen;
   const Real* fx_scen_p = a.fext + scen;
-  if (!EMEM && n_t > 0) e_next = __ldg(e_scen);
+#pragma unroll
+  for (int gl = 0; gl < GPL; ++gl) {
+    esc[gl] = (!EMEM && a.e_scale) ? a.e_scale[(long long)(g0 + gl) * ld + m] : Real(1);
+    e_next[gl] = (!EMEM && n_t > 0) ? __ldg(e_scen + gl * scen_gstride) : Real(0);
+  }
   if (fx_scen && n_t > 0) fx_next = __ldg(fx_scen_p);
 
   // ---------------- one time step ------------------------------------------------------------------
   auto step = [&](const int t, const uint32_t tt_off) {
-    Real e, fx = 0;
-    if (EMEM) {
-      e = lds(e_addr + tt_off, Real());
-    } else {
-      e = e_next * esc;
-      e_next = __ldg(e_scen + (long long)min(t + 1, n_t - 1) * a.n_scen);
-    }
+    Real fx = 0;
     if (fx_member) fx = lds(f_addr + tt_off, Real());
     if (fx_scen) {
       fx = fx_next;
       fx_next = __ldg(fx_scen_p + (long long)min(t + 1, n_t - 1) * a.n_scen);
     }
-    // ---- alpha_val: state at t-1 -> alpha, 1/alpha
-    Real alpha, inva;
-    if (AMODE == UFAIR_ALPHA_ONE) {
-      alpha = Real(1);
-      inva = Real(1);
-    } else {
-      Real u = fma(PAR(P_RHOU), Gcum, fma(PAR(P_WR), sumR, fma(PAR(P_RHOT), Tprev, PAR(P_RHO0))));
-      const Real umax = PAR(P_UMAX);
-      u = (u > umax) ? umax : u;
-      alpha = (AMODE == UFAIR_ALPHA_SINH) ? PAR(P_X0) * M::sinh_pair(u) : M::exp_(u);
-      if (AMODE == UFAIR_ALPHA_NEWTON) {
-        const Real iirf = (u - PAR(P_X1)) * PAR(P_X0);
-        const Real invc = PAR(P_X2);
-        for (int it = 0; it < a.newton_iters; ++it) {
-          const Real ia = M::rcp(alpha);
-          Real f = -iirf, fp = 0;
+    Real Fsum = 0;
 #pragma unroll
-          for (int q = 0; q < 4; ++q) {
-            const Real z = PAR(P_K0 + q) * hdt * ia;
-            const Real mz = M::decay(z);
-            const Real at = PAR(P_KA0 + q) * invc;  // a_i tau_i
-            f = fma(at * alpha, mz, f);
-            fp = fma(at, mz - z * (Real(1) - mz), fp);
-          }
-          const Real an = alpha - f * M::rcp(fp);
-          alpha = M::fmax_(an, Real(0.5) * alpha);
-        }
+    for (int gl = 0; gl < GPL; ++gl) {
+      Real e;
+      if (EMEM) {
+        e = lds(e_addr + tt_off + (uint32_t)gl * GROW, Real());
+      } else {
+        e = e_next[gl] * esc[gl];
+        e_next[gl] = __ldg(e_scen + gl * scen_gstride + (long long)min(t + 1, n_t - 1) * a.n_scen);
       }
-      inva = M::rcp(alpha);
+      // ---- alpha_val: state at t-1 -> alpha, 1/alpha
+      Real alpha, inva;
+      if (AMODE == UFAIR_ALPHA_ONE) {
+        alpha = Real(1);
+        inva = Real(1);
+      } else {
+        const Real rho0 = HOT_SMEM ? PARG(gl, WS::G_HOT + H_RHO0) : hot[gl][H_RHO0];
+        const Real rhoU = HOT_SMEM ? PARG(gl, WS::G_HOT + H_RHOU) : hot[gl][H_RHOU];
+        const Real wR = HOT_SMEM ? PARG(gl, WS::G_HOT + H_WR) : hot[gl][H_WR];
+        const Real rhoT = HOT_SMEM ? PARG(gl, WS::G_HOT + H_RHOT) : hot[gl][H_RHOT];
+        const Real umax = HOT_SMEM ? PARG(gl, WS::G_HOT + H_UMAX) : hot[gl][H_UMAX];
+        Real u = fma(rhoU, Gcum[gl], fma(wR, sumR[gl], fma(rhoT, Tprev, rho0)));
+        u = (u > umax) ? umax : u;
+        alpha = (AMODE == UFAIR_ALPHA_SINH) ? PARG(gl, WS::G_X0) * M::sinh_pair(u) : M::exp_(u);
+        if (AMODE == UFAIR_ALPHA_NEWTON) {
+          const Real iirf = (u - PARG(gl, WS::G_X0 + 1)) * PARG(gl, WS::G_X0);
+          const Real invc = PARG(gl, WS::G_X0 + 2);
+          for (int it = 0; it < a.newton_iters; ++it) {
+            const Real ia = M::rcp(alpha);
+            Real f = -iirf, fp = 0;
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              const Real z = PARG(gl, G_K0 + q) * hdt * ia;
+              const Real mz = M::decay(z);
+              const Real at = PARG(gl, G_KA0 + q) * invc;  // a_i tau_i
+              f = fma(at * alpha, mz, f);
+              fp = fma(at, mz - z * (Real(1) - mz), fp);
+            }
+            const Real an = alpha - f * M::rcp(fp);
+            alpha = M::fmax_(an, Real(0.5) * alpha);
+          }
+        }
+        inva = M::rcp(alpha);
+      }
+      // ---- step_conc: relax each pool toward its equilibrium  E alpha c a_i tau_i
+      const Real ea = e * alpha;
+      Real mq[4];
+#pragma unroll
+      for (int q = 0; q < 4; ++q)
+        mq[q] = (AMODE == UFAIR_ALPHA_ONE) ? PARG(gl, G_K0 + q) : M::decay(PARG(gl, G_K0 + q) * inva);
+#pragma unroll
+      for (int q = 0; q < 4; ++q) R[gl][q] = fma(mq[q], fma(ea, PARG(gl, G_KA0 + q), -R[gl][q]), R[gl][q]);
+      Gcum[gl] = fma(e, dt, Gcum[gl]);
+      sumR[gl] = (R[gl][0] + R[gl][1]) + (R[gl][2] + R[gl][3]);
+      const Real C = PARG(gl, G_C0) + sumR[gl];
+      // ---- step_forc
+      Real F = PARG(gl, G_F2) * sumR[gl];
+      if (need_log[gl]) F += M::mask(PARG(gl, G_F1) * M::log_(C * PARG(gl, G_INVC0)), mk1[gl]);
+      if (need_sqrt[gl]) F += M::mask(PARG(gl, G_F3) * (M::sqrt_(C) - PARG(gl, G_SQRTC0)), mk3[gl]);
+      if (wm & UFAIR_OUT_C) st_stream(pC + gl * gstride, C);
+      if (wm & UFAIR_OUT_RF) st_stream(pRF + gl * gstride, F);
+      if (wm & UFAIR_OUT_ALPHA) st_stream(pA + gl * gstride, alpha);
+      Fsum = (gl == 0) ? F : Fsum + F;
     }
-    // ---- step_conc: relax each pool toward its equilibrium  E alpha c a_i tau_i
-    const Real ea = e * alpha;
-    {
-      const Real m0_ = (AMODE == UFAIR_ALPHA_ONE) ? PAR(P_K0 + 0) : M::decay(PAR(P_K0 + 0) * inva);
-      const Real m1_ = (AMODE == UFAIR_ALPHA_ONE) ? PAR(P_K0 + 1) : M::decay(PAR(P_K0 + 1) * inva);
-      const Real m2_ = (AMODE == UFAIR_ALPHA_ONE) ? PAR(P_K0 + 2) : M::decay(PAR(P_K0 + 2) * inva);
-      const Real m3_ = (AMODE == UFAIR_ALPHA_ONE) ? PAR(P_K0 + 3) : M::decay(PAR(P_K0 + 3) * inva);
-      R0 = fma(m0_, fma(ea, PAR(P_KA0 + 0), -R0), R0);
-      R1 = fma(m1_, fma(ea, PAR(P_KA0 + 1), -R1), R1);
-      R2 = fma(m2_, fma(ea, PAR(P_KA0 + 2), -R2), R2);
-      R3 = fma(m3_, fma(ea, PAR(P_KA0 + 3), -R3), R3);
-    }
-    Gcum = fma(e, dt, Gcum);
-    sumR = (R0 + R1) + (R2 + R3);
-    const Real C = PAR(P_C0) + sumR;
-    // ---- step_forc
-    Real F = PAR(P_F2) * sumR;
-    if (need_log) {
-      const Real lt = PAR(P_F1) * M::log_(C * PAR(P_INVC0));
-      F += M::mask(lt, mk1);
-    }
-    if (need_sqrt) {
-      const Real st = PAR(P_F3) * (M::sqrt_(C) - PAR(P_SQRTC0));
-      F += M::mask(st, mk3);
-    }
-    if (wm & UFAIR_OUT_C) st_stream(pC, C);
-    if (wm & UFAIR_OUT_RF) st_stream(pRF, F);
-    if (wm & UFAIR_OUT_ALPHA) st_stream(pA, alpha);
     pC += ld;
     pRF += ld;
     pA += ld;
-    // ---- total forcing of the member: fixed order g = 0..NGAS-1, identical in its NGAS lanes
-    Real Ftot = fx;
+    // ---- total forcing of the member, gases in fixed order; external forcing last (as the oracle)
+    Real Ftot;
+    if (GROUPS == 1) {
+      Ftot = Fsum + fx;
+    } else {
+      Ftot = __shfl_sync(FULL, Fsum, i);
 #pragma unroll
-    for (int gg = 0; gg < NGAS; ++gg) Ftot += __shfl_sync(FULL, F, gg * MW + i);
-    // ---- step_temp (computed redundantly, bit-identically, by the NGAS lanes of a member)
-    const Real s0 = fma(PAR(P_QM0), Ftot, S0 * PAR(P_DEC0));
-    const Real s1 = fma(PAR(P_QM1), Ftot, S1 * PAR(P_DEC1));
+      for (int gg = 1; gg < GROUPS; ++gg) Ftot += __shfl_sync(FULL, Fsum, gg * MW + i);
+      Ftot += fx;
+    }
+    // ---- step_temp (with GROUPS > 1 computed redundantly, bit-identically, by a member's lanes)
+    const Real s0 = fma(PART(T_QM0), Ftot, S0 * PART(T_DEC0));
+    const Real s1 = fma(PART(T_QM1), Ftot, S1 * PART(T_DEC1));
     const Real T = t_mid ? Real(0.5) * ((S0 + s0) + (S1 + s1)) : (s0 + s1);
     S0 = s0;
     S1 = s1;
     Tprev = T;
     if (wm & UFAIR_OUT_T) st_stream(pT, T);
     pT += ld;
-    if (wm & 16u) {  // gas-0 lane of a real member: one histogram count
+    if (wm & 16u) {  // owner lane of a real member: one histogram count
       const Real x = M::bin_x(T, a.hist_lo, a.hist_invw);
       if (x == x) {
         const int b = max(0, min(bins_m1, M::floor_to_int(x)));
@@ -480,19 +512,22 @@ __global__ void __launch_bounds__(kWarps * 32, min_blocks(sizeof(Real)))
   // ---------------- epilogue: final state (checkpoint / resume) ---------------------------------
   if (a.state_out && active) {
     Real* so = a.state_out;
-    so[(long long)(5 * g + 0) * ld + m] = R0;
-    so[(long long)(5 * g + 1) * ld + m] = R1;
-    so[(long long)(5 * g + 2) * ld + m] = R2;
-    so[(long long)(5 * g + 3) * ld + m] = R3;
-    so[(long long)(5 * g + 4) * ld + m] = Gcum;
-    if (g == 0) {
+#pragma unroll
+    for (int gl = 0; gl < GPL; ++gl) {
+#pragma unroll
+      for (int q = 0; q < 4; ++q) so[(long long)(5 * (g0 + gl) + q) * ld + m] = R[gl][q];
+      so[(long long)(5 * (g0 + gl) + 4) * ld + m] = Gcum[gl];
+    }
+    if (g0 == 0) {
       so[(long long)(5 * NGAS + 0) * ld + m] = S0;
       so[(long long)(5 * NGAS + 1) * ld + m] = S1;
       so[(long long)(5 * NGAS + 2) * ld + m] = Tprev;
     }
   }
-#undef PAR
-#undef SETPAR
+#undef PARG
+#undef SETG
+#undef PART
+#undef SETT
 }
 
 // one launcher per (Real, NGAS, AMODE); defined in ufair_inst_*.cu
@@ -504,7 +539,7 @@ cudaError_t launch_integrate(const KArgs<Real>& a, const CUtensorMap& tmE, const
   cudaError_t launch_integrate<Real, NGAS, AMODE>(const KArgs<Real>& a, const CUtensorMap& tmE,                    \
                                                   const CUtensorMap& tmF, cudaStream_t stream) {                   \
     using WS = WarpSmem<Real, NGAS, AMODE>;                                                                        \
-    const size_t smem = WS::bytes_per_cta;                                                                         \
+    const size_t smem = (size_t)WS::bytes(a.fext_mode == UFAIR_FEXT_MEMBER) * kWarps;                                                                      \
     auto kern = (a.e_mode == UFAIR_E_MEMBER) ? ufair_integrate_kernel<Real, NGAS, AMODE, true>                     \
                                               : ufair_integrate_kernel<Real, NGAS, AMODE, false>;                  \
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);            \

@@ -168,6 +168,10 @@ int ufair_run_f32(const ufair_desc* d, void* stream);
 
 /* Zero (and initialise the min/max sentinels of) the private statistics buffers. */
 int ufair_stats_reset(const ufair_desc* d, void* stream);
+/* Second pass of the statistics: fold the T rows ufair_run_* just wrote (d->out_T, same
+ * descriptor, same stream) into moments_private.  One call per ufair_run_* call when stats == 1. */
+int ufair_stats_moments_f64(const ufair_desc* d, void* stream);
+int ufair_stats_moments_f32(const ufair_desc* d, void* stream);
 /* Fold the private copies: hist[hist_rows][hist_bins] (uint64 counts) and
  * moments[hist_rows][UFAIR_MOM_COUNT] (sum, sumsq, min, max as doubles). */
 int ufair_stats_finalize(const ufair_desc* d, uint64_t* hist, double* moments, void* stream);
