@@ -40,7 +40,7 @@ METRIC = "ensemble member-timesteps/sec"
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--members-per-gpu", type=int, default=1_250_000)
@@ -319,9 +319,11 @@ def main():
         flops_per_launch = FLOPS_PER_STEP * float(M) * n_t
         a_hbm = bytes_per_launch / (kernel_ms * 1e-3) / 1e9
         a_fp = flops_per_launch / (kernel_ms * 1e-3) / 1e12
-        traffic = None
+        traffic = None  # DRAM bytes per launch, scaled from the committed ncu --set full capture
         try:
-            traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get(args.precision)
+            tj = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get(args.precision)
+            if tj and spec is not None and outs == ("C", "RF", "T"):
+                traffic = tj["bytes_per_member_step"] * float(M) * n_t
         except Exception:
             pass
         t_hbm, t_fp = bytes_per_launch / (hbm_peak * 1e9), flops_per_launch / (fpeak * 1e12)
@@ -344,7 +346,8 @@ def main():
     # ---- e2e: the public host-buffer API, pinned host inputs, H2D + kernel + D2H of every output
     if not args.no_e2e:
         Me = min(args.e2e_members, M)
-        pin = lambda x: x.cpu().pin_memory()
+        hdt = torch.float64 if args.precision == "f64" else torch.float32
+        pin = lambda x: x.to(hdt).cpu().pin_memory()   # host arrays already in the run's precision
         Eh, gph, tph = pin(E[:, :, :Me]), pin(gp[:, :, :Me]), pin(tp[:, :Me])
         outs = ("C", "RF", "T")
         out = conc.pinned_result(N_GAS, n_t, Me, outputs=outs, stats=spec, precision=args.precision)
