@@ -159,10 +159,19 @@ class ClockSampler:
 # ------------------------------------------------------------------------------------------------
 # CPU arm: the oracle on the host cores (the only place bench.py executes oracle/)
 # ------------------------------------------------------------------------------------------------
+def host_threads():
+    """Host threads the CPU arm may use: the cores this process can run on (torchrun exports
+    OMP_NUM_THREADS=1, which is about the GPU ranks, not about this leg)."""
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except AttributeError:
+        return max(1, os.cpu_count() or 1)
+
+
 def cpu_oracle_rate(E, gp, tp, target_seconds, threads=0):
     """member-steps/s of the C oracle on a bounded sample (first members of the workload)."""
     from oracle import c_oracle as co
-    n_thr = co.max_threads() if threads <= 0 else threads
+    n_thr = host_threads() if threads <= 0 else threads
     n_t = E.shape[1]
     probe = min(E.shape[2], 64 * n_thr)
     t0 = time.perf_counter()
@@ -181,7 +190,7 @@ def run_reference(args):
         return
     from fiveeqscm_b200 import params as P
     from oracle import c_oracle as co
-    n_thr = co.max_threads()
+    n_thr = host_threads()
     n = max(256, 128 * n_thr)
     ens = P.sample_ensemble(n, n_t=args.n_t, dense_pools=not args.sparse)
     E = P.member_emissions(ens["scen"], ens["scen_idx"], ens["e_scale"])
@@ -234,6 +243,7 @@ def main():
     torch.cuda.set_device(local)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        os.environ["NCCL_DEBUG"] = os.environ.get("UFAIR_NCCL_DEBUG", "WARN")  # keep stdout to the one JSON line
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     n_gpus = world
     L = _abi.lib()
@@ -377,7 +387,7 @@ def main():
         ws.close()
 
     # ---- CPU baseline: the oracle on this box's cores, bounded sample of the same workload
-    if rank == 0 and not args.no_cpu:
+    if rank == 0 and world == 1 and not args.no_cpu:   # reported at N = 1 only
         n_cpu = min(M, 262144)
         rate, thr, n_used, secs = cpu_oracle_rate(E[:, :, :n_cpu].cpu().numpy(), gp[:, :, :n_cpu].cpu().numpy(),
                                                   tp[:, :n_cpu].cpu().numpy(), args.cpu_seconds)
