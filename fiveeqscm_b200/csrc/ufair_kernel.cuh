@@ -6,7 +6,7 @@
 //   GPL = 1    : ONE gas of one member    (default; MW = 32, 16, 10, 8 members per warp for 1..4
 //                                          gases; the NGAS lanes of a member add up their forcings
 //                                          with warp shuffles), or
-//   GPL = NGAS : ALL gases of one member  (MW = 32; build with -DUFAIR_GPL_ALL=1).
+//   GPL = NGAS : ALL gases of one member  (MW = 32; the FP32 default; -DUFAIR_GPL_ALL_F64=1 for FP64).
 //   Pools, cumulative emissions and the two thermal boxes stay in REGISTERS across the serial time
 //   loop; most derived per-member constants sit in shared memory ([param][lane], conflict-free
 //   LDS.64 at base + immediate) so the registers they would pin are free for instruction-level
@@ -47,17 +47,22 @@
 #include "../../include/ufair.h"
 #include "ufair_math.cuh"
 
-#ifndef UFAIR_GPL_ALL
-#define UFAIR_GPL_ALL 0  // 1: a lane integrates all gases of its member; 0: one gas per lane (measured faster)
+// 1: a lane integrates all gases of its member; 0: one gas per lane.  Measured: FP64 is faster with
+// one gas per lane (5 warps/SMSP beat the lower instruction count); in FP32 state is half as wide.
+#ifndef UFAIR_GPL_ALL_F64
+#define UFAIR_GPL_ALL_F64 0
+#endif
+#ifndef UFAIR_GPL_ALL_F32
+#define UFAIR_GPL_ALL_F32 1
 #endif
 #ifndef UFAIR_WARPS
 #define UFAIR_WARPS 4  // warps per CTA (a CTA is only a launch / shared-memory grouping)
 #endif
 #ifndef UFAIR_MINB_F64
-#define UFAIR_MINB_F64 (UFAIR_GPL_ALL ? 3 : 5)  // resident CTAs per SM the register allocator must allow
+#define UFAIR_MINB_F64 (UFAIR_GPL_ALL_F64 ? 3 : 5)  // resident CTAs per SM the register allocator must allow
 #endif
 #ifndef UFAIR_MINB_F32
-#define UFAIR_MINB_F32 (UFAIR_GPL_ALL ? 4 : 8)
+#define UFAIR_MINB_F32 (UFAIR_GPL_ALL_F32 ? 4 : 8)
 #endif
 #ifndef UFAIR_TT
 #define UFAIR_TT 8  // time steps per shared-memory tile (8 measured ~2 % faster than 4)
@@ -69,11 +74,13 @@ constexpr int kWarps = UFAIR_WARPS;
 constexpr int kTT = UFAIR_TT;
 constexpr int kStages = 2;  // tile ring depth
 
-constexpr int gases_per_lane(int n_gas) { return UFAIR_GPL_ALL ? n_gas : 1; }
+constexpr int gases_per_lane(int elem_size, int n_gas) {
+  return (elem_size == 8 ? UFAIR_GPL_ALL_F64 : UFAIR_GPL_ALL_F32) ? n_gas : 1;
+}
 // members per warp: rows of MW elements must be a multiple of 16 bytes for the TMA box
 constexpr int members_per_warp(int elem_size, int n_gas) {
-  const int q = 16 / elem_size;                          // elements per 16 bytes
-  const int groups = n_gas / gases_per_lane(n_gas);      // lanes per member
+  const int q = 16 / elem_size;                                    // elements per 16 bytes
+  const int groups = n_gas / gases_per_lane(elem_size, n_gas);     // lanes per member
   return (32 / groups) / q * q;
 }
 
@@ -177,7 +184,7 @@ constexpr size_t round128(size_t b) { return (b + 127) / 128 * 128; }
 
 // per-WARP shared memory, in bytes (every piece 128-byte aligned: tensor-map TMA destinations)
 template <typename Real, int NGAS, int AMODE> struct WarpSmem {
-  static constexpr int GPL = gases_per_lane(NGAS);
+  static constexpr int GPL = gases_per_lane(sizeof(Real), NGAS);
   static constexpr bool HOT_SMEM = (GPL == 1);
   static constexpr int MW = members_per_warp(sizeof(Real), NGAS);
   static constexpr int G_HOT = G_COLD;                            // first hot row (if in smem)
@@ -348,6 +355,7 @@ __global__ void __launch_bounds__(kWarps * 32, min_blocks(sizeof(Real)))
     S1 = si ? si[(long long)(5 * NGAS + 1) * ld + m] : Real(0);
     Tprev = si ? si[(long long)(5 * NGAS + 2) * ld + m] : Real(0);
   }
+  Real Ssum = S0 + S1;  // carried so that the mid-step mean costs one add
   __syncwarp();
 
   const int scen = (a.scen_idx != nullptr) ? a.scen_idx[m] : 0;
@@ -446,9 +454,11 @@ __global__ void __launch_bounds__(kWarps * 32, min_blocks(sizeof(Real)))
       sumR[gl] = (R[gl][0] + R[gl][1]) + (R[gl][2] + R[gl][3]);
       const Real C = PARG(gl, G_C0) + sumR[gl];
       // ---- step_forc
+      // (the log / sqrt VALUE is masked, not the product, so that a zero coefficient with an
+      // infinite or NaN function value -- C0 = 0 gases -- still contributes exactly zero)
       Real F = PARG(gl, G_F2) * sumR[gl];
-      if (need_log[gl]) F += M::mask(PARG(gl, G_F1) * M::log_(C * PARG(gl, G_INVC0)), mk1[gl]);
-      if (need_sqrt[gl]) F += M::mask(PARG(gl, G_F3) * (M::sqrt_(C) - PARG(gl, G_SQRTC0)), mk3[gl]);
+      if (need_log[gl]) F = fma(PARG(gl, G_F1), M::mask(M::log_(C * PARG(gl, G_INVC0)), mk1[gl]), F);
+      if (need_sqrt[gl]) F = fma(PARG(gl, G_F3), M::mask(M::sqrt_(C) - PARG(gl, G_SQRTC0), mk3[gl]), F);
       if (wm & UFAIR_OUT_C) st_stream(pC + gl * gstride, C);
       if (wm & UFAIR_OUT_RF) st_stream(pRF + gl * gstride, F);
       if (wm & UFAIR_OUT_ALPHA) st_stream(pA + gl * gstride, alpha);
@@ -470,9 +480,11 @@ __global__ void __launch_bounds__(kWarps * 32, min_blocks(sizeof(Real)))
     // ---- step_temp (with GROUPS > 1 computed redundantly, bit-identically, by a member's lanes)
     const Real s0 = fma(PART(T_QM0), Ftot, S0 * PART(T_DEC0));
     const Real s1 = fma(PART(T_QM1), Ftot, S1 * PART(T_DEC1));
-    const Real T = t_mid ? Real(0.5) * ((S0 + s0) + (S1 + s1)) : (s0 + s1);
+    const Real Snew = s0 + s1;
+    const Real T = t_mid ? Real(0.5) * (Ssum + Snew) : Snew;
     S0 = s0;
     S1 = s1;
+    Ssum = Snew;
     Tprev = T;
     if (wm & UFAIR_OUT_T) st_stream(pT, T);
     pT += ld;

@@ -69,8 +69,11 @@ template <> struct Math<double> {
   // m = 1 - exp(-x) for 0 <= x <= 1e15 (larger x, inf: NaN; NaN propagates).  2^n is clamped at
   // 2^-1000 in the integer domain, so the result saturates at exactly 1 without an FP64 compare.
   static __device__ __forceinline__ double decay(double x) {
-    int n;
-    double r = reduce(-x, n);
+    // single-constant reduction: ln2's low word shifts r by n * 2.3e-17, i.e. the result by
+    // <= 2^n * |n| * 2.3e-17 absolute -- below half an ulp of m for every n <= -1 (m >= 0.29)
+    double t = fma(-x, cK[0], cK[3]);
+    int n = __double2loint(t);
+    double r = fma(t - cK[3], cK[1], -x);
     double p = expm1_reduced(r);
     n = max(n, -1000);
     double s = __hiloint2double((1023 + n) << 20, 0);  // 2^n (exact)
@@ -86,27 +89,25 @@ template <> struct Math<double> {
     return __hiloint2double(__double2hiint(v) + (n << 20), __double2loint(v));
   }
 
-  // 1/a for positive normal a: MUFU.RCP64H seed + 2 Newton steps (4 DFMA), ~1 ulp.
+  // 1/a for positive normal a: MUFU.RCP64H seed y (relative error e ~ 2^-20) and one third-order
+  // step y (1 + e + e^2), error e^3: 3 DFMA, ~1 ulp.
   static __device__ __forceinline__ double rcp(double a) {
     double y;
     asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(a));
     double e = fma(-a, y, 1.0);
-    y = fma(y, e, y);
-    e = fma(-a, y, 1.0);
-    return fma(y, e, y);
+    return fma(y, fma(e, e, e), y);
   }
 
-  // sqrt(a) for a >= 0: MUFU.RSQ64H seed + 2 coupled Newton steps; sqrt(0) = 0; a < 0 -> NaN.
+  // sqrt(a) for a >= 0: MUFU.RSQ64H seed y, t = a y, e = 1 - t y, sqrt = t (1 + e/2 + 3 e^2 / 8),
+  // error 5 e^3 / 16: 5 FP64 ops.  sqrt(0) = 0 (integer test, no FP64 compare); a < 0 -> NaN.
   static __device__ __forceinline__ double sqrt_(double a) {
     double y;
     asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(a));
-    double g = a * y, h = 0.5 * y;
-    double r = fma(-g, h, 0.5);
-    g = fma(g, r, g);
-    h = fma(h, r, h);
-    r = fma(-g, h, 0.5);
-    g = fma(g, r, g);
-    return (a == 0.0) ? 0.0 : g;
+    double t = a * y;
+    double e = fma(-t, y, 1.0);
+    double p = fma(e, 0.375, 0.5) * e;
+    double g = fma(t, p, t);
+    return ((__double2hiint(a) << 1) | __double2loint(a)) == 0 ? 0.0 : g;
   }
 
   // log(y).  Positive normal y on the fast path; everything else takes the (never hot) libm call.
