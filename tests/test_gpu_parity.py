@@ -353,3 +353,64 @@ def test_full_size_shard_properties(api):
     res2 = api.run_ensemble(E, gp, tp, stats=spec, outputs=(), return_state=False)
     torch.cuda.synchronize()
     assert torch.equal(res2.hist, hist)
+
+
+def test_config2_full_size_fp64_vs_fp32(api):
+    """BASELINE configs[2]: 10^6-member perturbed-parameter ensemble x 4 scenarios, FP64 vs FP32.
+    Full size on the device (scenario-shared emissions, T + statistics only); the oracle checks a
+    slice, the two precisions are compared with each other everywhere (<= 1e-4 K)."""
+    import torch
+    M, n_t = 1_000_000, 736
+    ens = ensemble(8192, dense=True, seed=42)
+    reps = (M + 8191) // 8192
+    tile = lambda x: to_dev(x).repeat(*([1] * (x.ndim - 1)), reps)[..., :M].contiguous()
+    g = torch.Generator(device="cuda").manual_seed(7)
+    gp, tp = tile(ens["gas_params"]), tile(ens["thermal_params"])
+    gp[:, _abi.GP_R0] *= 1 + 0.02 * torch.randn(3, M, generator=g, device="cuda", dtype=torch.float64)
+    idx = torch.randint(0, 4, (M,), generator=g, device="cuda", dtype=torch.int32)
+    esc = 1 + 0.05 * torch.randn(3, M, generator=g, device="cuda", dtype=torch.float64)
+    scen = to_dev(ens["scen"])
+    kw = dict(scen_idx=idx, e_scale=esc, outputs=("T",), stats=api.HistSpec(), return_state=False)
+    r64 = api.run_ensemble(scen, gp, tp, precision="f64", **kw)
+    r32 = api.run_ensemble(scen, gp, tp, precision="f32", **kw)
+    torch.cuda.synchronize()
+    assert bool((r64.hist.sum(dim=1) == M).all()) and bool((r32.hist.sum(dim=1) == M).all())
+    assert float((r64.T - r32.T.double()).abs().max()) <= 1e-4
+    sl = slice(123_456, 123_456 + 256)
+    ref = co.oxfair(ens["scen"], to_np(gp[:, :, sl]), to_np(tp[:, sl]), scen_idx=to_np(idx[sl]), e_scale=to_np(esc[:, sl]))
+    assert field_relerr(to_np(r64.T[:, sl]), ref["T"]) < TOL64
+    # per-scenario means are ordered like the scenarios' cumulative emissions in 2500
+    T_end = r64.T[-1]
+    means = [float(T_end[idx == s].mean()) for s in range(4)]
+    assert means[1] > means[0] and means[2] > means[0] and means[3] < means[0]
+
+
+def test_config4_full_size_subannual(api):
+    """BASELINE configs[4]: dt = 0.1 yr, 10^6 members x 7360 steps (scenario-shared emissions, T only).
+    Size-independent properties: every histogram row counts every member, and two time chunks joined
+    through state_out/state_in reproduce the one-shot run bit for bit."""
+    import torch
+    M, n_t, dt = 1_000_000, 7360, 0.1
+    ens = ensemble(4096, n_t=n_t, dt=dt, dense=True, seed=9)
+    reps = (M + 4095) // 4096
+    tile = lambda x: to_dev(x).repeat(*([1] * (x.ndim - 1)), reps)[..., :M].contiguous()
+    gp, tp = tile(ens["gas_params"]), tile(ens["thermal_params"])
+    g = torch.Generator(device="cuda").manual_seed(11)
+    gp[:, _abi.GP_R0] *= 1 + 0.02 * torch.randn(3, M, generator=g, device="cuda", dtype=torch.float64)
+    idx = torch.randint(0, 4, (M,), generator=g, device="cuda", dtype=torch.int32)
+    scen = to_dev(ens["scen"])
+    spec = api.HistSpec(copies=8)
+    one = api.run_ensemble(scen, gp, tp, dt=dt, scen_idx=idx, outputs=("T",), stats=spec)
+    torch.cuda.synchronize()
+    assert bool((one.hist.sum(dim=1) == M).all())
+    T_one_tail = one.T[-64:].clone()
+    state_one = one.state.clone()
+    del one
+    cut = 3333                       # not a multiple of the tile length
+    a = api.run_ensemble(scen[:, :cut].contiguous(), gp, tp, dt=dt, scen_idx=idx, outputs=())
+    b = api.run_ensemble(scen[:, cut:].contiguous(), gp, tp, dt=dt, scen_idx=idx, outputs=("T",), state_in=a.state)
+    torch.cuda.synchronize()
+    assert torch.equal(b.T[-64:], T_one_tail) and torch.equal(b.state, state_one)
+    sl = slice(500_000, 500_000 + 64)
+    ref = co.oxfair(ens["scen"], to_np(gp[:, :, sl]), to_np(tp[:, sl]), dt=dt, scen_idx=to_np(idx[sl]))
+    assert field_relerr(to_np(b.T[-64:, sl]), ref["T"][-64:]) < TOL64

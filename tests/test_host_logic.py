@@ -136,3 +136,20 @@ def test_two_rank_gloo_reduction_matches_single_rank(tmp_path):
     for r, p in enumerate(procs):
         out, err = p.communicate(timeout=300)
         assert p.returncode == 0 and f"RANK_OK {r}" in out, err[-2000:]
+
+
+def test_bench_reference_arm_contract():
+    """`bench.py --impl reference` (the CPU arm: the C oracle on the host cores) prints ONE JSON line
+    with the contract's keys."""
+    import json
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1",
+                          "--warmup", "1"], capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stderr[-2000:]
+    lines = [l for l in out.stdout.splitlines() if l.strip()]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["metric"] == "ensemble member-timesteps/sec" and d["value"] > 0
+    assert d["higher_is_better"] is True and d["unit"] == "member-timesteps/s"
+    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1
+    assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["value"] == d["value"]
+    assert "workload" in d["config"]
