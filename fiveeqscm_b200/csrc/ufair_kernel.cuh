@@ -56,13 +56,13 @@
 #define UFAIR_GPL_ALL_F32 1
 #endif
 #ifndef UFAIR_WARPS
-#define UFAIR_WARPS 4  // warps per CTA (a CTA is only a launch / shared-memory grouping)
-#endif
-#ifndef UFAIR_MINB_F64
-#define UFAIR_MINB_F64 (UFAIR_GPL_ALL_F64 ? 3 : 5)  // resident CTAs per SM the register allocator must allow
+#define UFAIR_WARPS 1  // warps per CTA.  A CTA is only a launch / shared-memory grouping (warps never
+#endif                 // synchronise); single-warp CTAs measured ~2 % faster than 4 (finer refill)
+#ifndef UFAIR_MINB_F64  // resident WARPS per SM the register allocator must allow (CTAs = this / WARPS)
+#define UFAIR_MINB_F64 ((UFAIR_GPL_ALL_F64 ? 12 : 20) / UFAIR_WARPS)
 #endif
 #ifndef UFAIR_MINB_F32
-#define UFAIR_MINB_F32 (UFAIR_GPL_ALL_F32 ? 4 : 8)
+#define UFAIR_MINB_F32 ((UFAIR_GPL_ALL_F32 ? 16 : 32) / UFAIR_WARPS)
 #endif
 #ifndef UFAIR_TT
 #define UFAIR_TT 8  // time steps per shared-memory tile (8 measured ~2 % faster than 4)
@@ -240,6 +240,7 @@ __global__ void __launch_bounds__(kWarps * 32, min_blocks(sizeof(Real)))
 
   const bool fx_member = (a.fext_mode == UFAIR_FEXT_MEMBER);
   const bool fx_scen = (a.fext_mode == UFAIR_FEXT_SCENARIO);
+  const bool fx_any = fx_member || fx_scen;
   const bool use_tma = EMEM || fx_member;
 
   const uint32_t wbase = smem_u32(smem_raw) + (uint32_t)warp * WS::bytes(fx_member);
@@ -373,7 +374,7 @@ __global__ void __launch_bounds__(kWarps * 32, min_blocks(sizeof(Real)))
   const long long o_gas = (long long)g0 * gstride + m_raw;
   Real* pC = a.oC + o_gas;
   Real* pRF = a.oRF + o_gas;
-  Real* pA = a.oA + o_gas;
+  const long long dA = a.oA - a.oC;  // the (diagnostic) alpha output is addressed relative to pC
   Real* pT = a.oT + m_raw;
   unsigned int* hrow = a.stats ? a.hist + ((size_t)(wg % a.hist_copies) * a.hist_rows + a.hist_t0) * a.hist_bins : nullptr;
   const int bins_m1 = a.hist_bins - 1;
@@ -393,10 +394,12 @@ __global__ void __launch_bounds__(kWarps * 32, min_blocks(sizeof(Real)))
   // ---------------- one time step ------------------------------------------------------------------
   auto step = [&](const int t, const uint32_t tt_off) {
     Real fx = 0;
-    if (fx_member) fx = lds(f_addr + tt_off, Real());
-    if (fx_scen) {
-      fx = fx_next;
-      fx_next = __ldg(fx_scen_p + (long long)min(t + 1, n_t - 1) * a.n_scen);
+    if (fx_any) {  // one uniform branch when there is no external forcing at all
+      if (fx_member) fx = lds(f_addr + tt_off, Real());
+      if (fx_scen) {
+        fx = fx_next;
+        fx_next = __ldg(fx_scen_p + (long long)min(t + 1, n_t - 1) * a.n_scen);
+      }
     }
     Real Fsum = 0;
 #pragma unroll
@@ -461,12 +464,11 @@ __global__ void __launch_bounds__(kWarps * 32, min_blocks(sizeof(Real)))
       if (need_sqrt[gl]) F = fma(PARG(gl, G_F3), M::mask(M::sqrt_(C) - PARG(gl, G_SQRTC0), mk3[gl]), F);
       if (wm & UFAIR_OUT_C) st_stream(pC + gl * gstride, C);
       if (wm & UFAIR_OUT_RF) st_stream(pRF + gl * gstride, F);
-      if (wm & UFAIR_OUT_ALPHA) st_stream(pA + gl * gstride, alpha);
+      if (wm & UFAIR_OUT_ALPHA) st_stream(pC + dA + gl * gstride, alpha);
       Fsum = (gl == 0) ? F : Fsum + F;
     }
     pC += ld;
     pRF += ld;
-    pA += ld;
     // ---- total forcing of the member, gases in fixed order; external forcing last (as the oracle)
     Real Ftot;
     if (GROUPS == 1) {

