@@ -76,14 +76,14 @@ def test_oracle_struct_layout_matches_c(built):
 
 
 def test_product_never_imports_the_oracle():
-    pkg = os.path.join(ROOT, "fiveeqscm_b200")
-    for dirpath, _, files in os.walk(pkg):
-        for f in files:
-            if f.endswith((".py", ".cu", ".cuh", ".h")):
-                text = open(os.path.join(dirpath, f)).read()
-                assert "oracle" not in text.replace("the oracle", "").replace("float64 oracle", "").lower() or \
-                    "import oracle" not in text and "from oracle" not in text, f
-    for f in os.listdir(os.path.join(ROOT, "U_FaIR")):
-        if f.endswith(".py"):
-            text = open(os.path.join(ROOT, "U_FaIR", f)).read()
-            assert "import oracle" not in text and "from oracle" not in text
+    """The oracle is test infrastructure: nothing under the product packages may import, load or
+    link it (no `import oracle`, no libufair_oracle, no ufo_* symbol)."""
+    for pkg in ("fiveeqscm_b200", "U_FaIR", "include"):
+        for dirpath, _, files in os.walk(os.path.join(ROOT, pkg)):
+            if os.path.basename(dirpath).startswith("build"):
+                continue
+            for f in files:
+                if f.endswith((".py", ".cu", ".cuh", ".h")) or f == "Makefile":
+                    text = open(os.path.join(dirpath, f)).read()
+                    for needle in ("import oracle", "from oracle", "libufair_oracle", "ufo_run", "c_oracle"):
+                        assert needle not in text, f"{os.path.join(dirpath, f)} mentions {needle!r}"
