@@ -362,7 +362,11 @@ __global__ void __launch_bounds__(kWarps * 32, min_blocks(sizeof(Real)))
   const int scen = (a.scen_idx != nullptr) ? a.scen_idx[m] : 0;
   const Real dt = (Real)a.dt;
   const Real hdt = (Real)(a.h / a.dt);
-  const bool t_mid = (a.t_mode == UFAIR_T_MID);
+  // T = wOld (S1 + S2)_old + wNew (S1 + S2)_new: (1/2, 1/2) is the mid-step mean, (0, 1) the end value;
+  // bit-identical to the select it replaces because scaling by 1/2 is exact
+  const Real wOld = (a.t_mode == UFAIR_T_MID) ? Real(0.5) : Real(0);
+  const Real wNew = (a.t_mode == UFAIR_T_MID) ? Real(0.5) : Real(1);
+  const bool clamp = a.clamp != 0;
 
   // output predicates packed in one register; running output pointers (gas g0; + gl * gstride)
   const bool owner = active && (g0 == 0);  // the lane that owns the member's T / histogram count
@@ -421,9 +425,11 @@ __global__ void __launch_bounds__(kWarps * 32, min_blocks(sizeof(Real)))
         const Real rhoU = HOT_SMEM ? PARG(gl, WS::G_HOT + H_RHOU) : hot[gl][H_RHOU];
         const Real wR = HOT_SMEM ? PARG(gl, WS::G_HOT + H_WR) : hot[gl][H_WR];
         const Real rhoT = HOT_SMEM ? PARG(gl, WS::G_HOT + H_RHOT) : hot[gl][H_RHOT];
-        const Real umax = HOT_SMEM ? PARG(gl, WS::G_HOT + H_UMAX) : hot[gl][H_UMAX];
         Real u = fma(rhoU, Gcum[gl], fma(wR, sumR[gl], fma(rhoT, Tprev, rho0)));
-        u = (u > umax) ? umax : u;
+        if (clamp) {  // uniform: the iIRF ceiling costs nothing when it is switched off
+          const Real umax = HOT_SMEM ? PARG(gl, WS::G_HOT + H_UMAX) : hot[gl][H_UMAX];
+          u = (u > umax) ? umax : u;
+        }
         alpha = (AMODE == UFAIR_ALPHA_SINH) ? PARG(gl, WS::G_X0) * M::sinh_pair(u) : M::exp_(u);
         if (AMODE == UFAIR_ALPHA_NEWTON) {
           const Real iirf = (u - PARG(gl, WS::G_X0 + 1)) * PARG(gl, WS::G_X0);
@@ -483,7 +489,7 @@ __global__ void __launch_bounds__(kWarps * 32, min_blocks(sizeof(Real)))
     const Real s0 = fma(PART(T_QM0), Ftot, S0 * PART(T_DEC0));
     const Real s1 = fma(PART(T_QM1), Ftot, S1 * PART(T_DEC1));
     const Real Snew = s0 + s1;
-    const Real T = t_mid ? Real(0.5) * (Ssum + Snew) : Snew;
+    const Real T = fma(wNew, Snew, wOld * Ssum);
     S0 = s0;
     S1 = s1;
     Ssum = Snew;
