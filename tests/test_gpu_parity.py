@@ -414,3 +414,24 @@ def test_config4_full_size_subannual(api):
     sl = slice(500_000, 500_000 + 64)
     ref = co.oxfair(ens["scen"], to_np(gp[:, :, sl]), to_np(tp[:, sl]), dt=dt, scen_idx=to_np(idx[sl]))
     assert field_relerr(to_np(b.T[-64:, sl]), ref["T"][-64:]) < TOL64
+
+
+def test_host_pipeline_fp32_and_output_reuse(api):
+    """FP32 through the host pipeline == FP32 on the device; `out=` reuses the caller's (pinned) buffers."""
+    ens = ensemble(3000, n_t=64, dense=True)
+    spec = api.HistSpec(copies=5)
+    dev = _run_dev(api, ens, precision="f32", stats=spec)
+    out = api.pinned_result(3, 64, 3000, stats=spec, precision="f32")
+    ws = api.Workspace(0, 1024)
+    r1 = api.run_ensemble(ens["E"], ens["gas_params"], ens["thermal_params"], precision="f32", stats=spec,
+                          workspace=ws, out=out)
+    assert r1 is out and r1.T.dtype == np.float32
+    t_ptr = r1.T.ctypes.data
+    for k in ("C", "RF", "T", "state"):
+        np.testing.assert_array_equal(getattr(r1, k), to_np(getattr(dev, k)))
+    np.testing.assert_array_equal(r1.hist, to_np(dev.hist))
+    r2 = api.run_ensemble(ens["E"], ens["gas_params"], ens["thermal_params"], precision="f32", stats=spec,
+                          workspace=ws, out=out)
+    assert r2.T.ctypes.data == t_ptr            # same buffer, refilled
+    np.testing.assert_array_equal(r2.T, to_np(dev.T))
+    ws.close()
