@@ -117,11 +117,11 @@ template <> struct Math<double> {
     // (flushed), NaN for negatives, y itself for +inf / NaN.  Kept tiny so it stays predicated.
     if (__builtin_expect((unsigned)(hi - 0x00100000) >= 0x7fe00000u, 0))
       return (unsigned)(hi & 0x7fffffff) < 0x00100000u ? -INFINITY : (hi < 0 ? __longlong_as_double(0x7ff8000000000000ll) : y);
-    int e = (hi >> 20) - 1023;
-    int mh = (hi & 0x000fffff) | 0x3ff00000;  // mantissa in [1,2)
-    const int up = mh > 0x3ff6a09e;            // > sqrt(2): halve
-    mh -= up << 20;
-    e += up;
+    // y = 2^e m with m in [sqrt(1/2), sqrt(2)): bias the high word so the exponent field rolls over
+    // exactly at the mantissa of sqrt(2) (0x6a09e...), the fdlibm normalisation -- 4 integer ops
+    const int hx = hi + (0x3ff00000 - 0x3fe6a09e);
+    const int e = (hx >> 20) - 1023;
+    const int mh = (hx & 0x000fffff) + 0x3fe6a09e;
     double m = __hiloint2double(mh, lo);
     double f = m - 1.0;
     double d = m + 1.0, rc = rcp(d);
