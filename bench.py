@@ -32,7 +32,7 @@ import numpy as np  # noqa: E402
 
 N_GAS = 3
 # algorithmic work per member-step (BASELINE.md section 5 / DESIGN.md): 3 gases
-BYTES_PER_STEP_F64 = 80.0            # 3 E in + 3 C + 3 RF + 1 T out, 8 B each
+#   bytes: 3 E in + 3 C + 3 RF + 1 T out = 10 words (80 B in f64, 40 B in f32)
 FLOPS_PER_STEP = 751.0               # 163 simple + 15 exp(28) + 3 log(36) + 3 sqrt(10) + 3 div(10)
 METRIC = "ensemble member-timesteps/sec"
 

@@ -23,7 +23,10 @@
 //     v6 = GPL_ALL: a lane integrates all gases of its member again, now with smem constants (no
 //        redundant thermal step, no shuffles, no idle lanes: 27 instr per member-step instead of
 //        33.5) -- but 168 regs leave 3 warps/SMSP and IPC drops to 0.45: 47.8 ms.  Thread-level
-//        parallelism beats instruction count here, so GPL = 1 stays the default.
+//        parallelism beats instruction count here, so GPL = 1 stays the FP64 default (FP32, with
+//        half-width state, runs GPL = NGAS at 4 warps/SMSP: 26.4 -> 14.1 ms).
+//     final round 1: cheaper rcp / sqrt / log, single-constant decay reduction, single-warp CTAs,
+//        TT = 8: 293 instr per warp-step, FP64 pipe 62 %, 36.4 ms alone / 36.9-39.4 ms sustained.
 //   The loop body is alpha_val -> step_conc -> step_forc -> step_temp, the names the reference
 //   reserves in .coveragerc:12-19; `oxfair` is ONE launch.
 //
