@@ -108,6 +108,7 @@ SIGNATURES = {
     "ufair_stats_moments_f64": (C.c_int, [C.POINTER(UfairDesc), _vp]),
     "ufair_stats_moments_f32": (C.c_int, [C.POINTER(UfairDesc), _vp]),
     "ufair_stats_finalize": (C.c_int, [C.POINTER(UfairDesc), _vp, _vp, _vp]),
+    "ufair_hist_percentiles": (C.c_int, [_vp, _i32, _i32, _dbl, _dbl, _vp, _i32, _vp, _vp]),
     "ufair_g1g0_f64": (C.c_int, [_vp, _vp, _i64, _i64, _dbl, _i32, _vp, _vp, _vp]),
     "ufair_kq_f64": (C.c_int, [_vp, _vp, _vp, _vp, _dbl, _i64, _vp, _vp, _vp]),
     "ufair_hfc_pulse_f64": (C.c_int, [_vp, _vp, _vp, _i64, _vp]),

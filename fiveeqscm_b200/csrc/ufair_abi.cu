@@ -297,6 +297,37 @@ __global__ void stats_finalize_kernel(const unsigned int* hp, const double* mp, 
   }
 }
 
+// one thread per (row, percentile): walk the row's CDF (exact integers), interpolate inside the bin.
+// Same operations in the same order as oracle/ufair_oracle.py percentiles_from_hist (no FMA).
+__global__ void percentiles_kernel(const unsigned long long* __restrict__ hist, int rows, int bins, double lo, double hi,
+                                   const double* __restrict__ pcts, int n_pct, double* __restrict__ out) {
+  const long long id = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (id >= (long long)rows * n_pct) return;
+  const int row = (int)(id / n_pct), j = (int)(id % n_pct);
+  const unsigned long long* h = hist + (size_t)row * bins;
+  unsigned long long tot = 0;
+  for (int b = 0; b < bins; ++b) tot += h[b];
+  const double target = __dmul_rn((double)tot, __ddiv_rn(pcts[j], 100.0));
+  unsigned long long cum = 0, prev = 0;
+  int k = bins - 1;
+  for (int b = 0; b < bins; ++b) {  // k = number of bins whose CDF is < target, capped at bins - 1
+    prev = cum;
+    cum += h[b];
+    if (!((double)cum < target)) {
+      k = b;
+      break;
+    }
+  }
+  if (k == bins - 1 && (double)cum < target) {  // ran off the end: recompute prev for the last bin
+    prev = cum - h[bins - 1];
+  }
+  const double cnt = (double)h[k];
+  double frac = cnt > 0.0 ? __ddiv_rn(__dsub_rn(target, (double)prev), cnt) : 0.0;
+  frac = fmin(fmax(frac, 0.0), 1.0);
+  const double w = __ddiv_rn(__dsub_rn(hi, lo), (double)bins);
+  out[id] = __dadd_rn(lo, __dmul_rn(__dadd_rn((double)k, frac), w));
+}
+
 static int check_stats_desc(const ufair_desc* d) {
   if (!d || d->struct_size != sizeof(ufair_desc)) return set_error(UFAIR_ERR_ARG, "bad descriptor");
   if (d->hist_bins < 1 || d->hist_copies < 1 || d->hist_rows < 1 || !d->hist_private || !d->moments_private)
@@ -476,6 +507,18 @@ int ufair_hfc_pulse_f64(const double* e0, const double* time, double* out, int64
   hfc_pulse_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(e0, time, out, n);
   cudaError_t e = cudaGetLastError();
   return e == cudaSuccess ? UFAIR_OK : cuda_error(e, "hfc_pulse_kernel");
+}
+
+int ufair_hist_percentiles(const uint64_t* hist, int32_t rows, int32_t bins, double lo, double hi, const double* pcts,
+                           int32_t n_pct, double* out, void* stream) {
+  if (rows < 0 || bins < 1 || n_pct < 0 || !(hi > lo)) return set_error(UFAIR_ERR_ARG, "bad histogram spec");
+  if (rows == 0 || n_pct == 0) return UFAIR_OK;
+  if (!hist || !pcts || !out) return set_error(UFAIR_ERR_ARG, "NULL pointer");
+  const long long n = (long long)rows * n_pct;
+  percentiles_kernel<<<(unsigned)((n + 127) / 128), 128, 0, (cudaStream_t)stream>>>(
+      (const unsigned long long*)hist, rows, bins, lo, hi, pcts, n_pct, out);
+  cudaError_t e = cudaGetLastError();
+  return e == cudaSuccess ? UFAIR_OK : cuda_error(e, "percentiles_kernel");
 }
 
 int ufair_math_probe_f64(int op, const double* x, double* y, int64_t n, void* stream) {

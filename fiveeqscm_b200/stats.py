@@ -37,6 +37,25 @@ def percentiles(hist, lo: float, hi: float, pcts):
     return out
 
 
+def percentiles_device(hist, lo: float, hi: float, pcts):
+    """Same as :func:`percentiles`, computed on the GPU (libufair `ufair_hist_percentiles`) from a
+    device histogram [n_t][bins] (int64 counts, e.g. the all-reduced one); returns a device tensor
+    [n_t][len(pcts)].  Bit-identical to the host version."""
+    import torch
+
+    from . import _abi
+    if not (isinstance(hist, torch.Tensor) and hist.is_cuda and hist.dtype == torch.int64):
+        raise ValueError("hist must be a CUDA int64 tensor [n_t][bins]")
+    h = hist.contiguous()
+    p = torch.as_tensor(list(pcts), dtype=torch.float64, device=h.device)
+    out = torch.empty(h.shape[0], p.numel(), dtype=torch.float64, device=h.device)
+    with torch.cuda.device(h.device):
+        _abi.check(_abi.lib().ufair_hist_percentiles(h.data_ptr(), h.shape[0], h.shape[1], float(lo), float(hi),
+                                                     p.data_ptr(), p.numel(), out.data_ptr(),
+                                                     torch.cuda.current_stream(h.device).cuda_stream))
+    return out
+
+
 def mean_std(moments, n_member: int):
     """(mean, std) per step from moments [n_t][4] = sum, sumsq, min, max."""
     m = _np(moments)

@@ -176,6 +176,12 @@ int ufair_stats_moments_f32(const ufair_desc* d, void* stream);
  * moments[hist_rows][UFAIR_MOM_COUNT] (sum, sumsq, min, max as doubles). */
 int ufair_stats_finalize(const ufair_desc* d, uint64_t* hist, double* moments, void* stream);
 
+/* Percentiles read off the (reduced) per-step histogram CDF, linear inside the bin:
+ * out[row][j] = percentile pcts[j] (0..100) of row `row`; hist: [rows][bins] counts, pcts: [n_pct]
+ * (device), out: [rows][n_pct] (device).  Bit-identical to the oracle's percentiles_from_hist. */
+int ufair_hist_percentiles(const uint64_t* hist, int32_t rows, int32_t bins, double lo, double hi,
+                           const double* pcts, int32_t n_pct, double* out, void* stream);
+
 /* ---- parameter preparation (g_1, g_0, k_q in the reference's naming) ---- */
 /* a, tau: [4][ld]; out g1, g0: [ld]. alpha_mode selects the g0 form (EXP/NEWTON vs SINH). */
 int ufair_g1g0_f64(const double* a, const double* tau, int64_t n_member, int64_t ld_member,

@@ -225,6 +225,11 @@ def test_histogram_bit_exact_and_moments(api):
     pct = S.percentiles(res.hist, spec.lo, spec.hi, [5, 50, 95])
     direct = np.percentile(T, [5, 50, 95], axis=1).T
     assert np.max(np.abs(pct - direct)) < 2 * (spec.hi - spec.lo) / spec.bins
+    # the device percentile kernel is bit-identical to the oracle's CDF walk (and to the host one)
+    pcts = [0.0, 1.0, 5.0, 17.0, 50.0, 83.0, 95.0, 99.9, 100.0]
+    pct_dev = to_np(S.percentiles_device(res.hist, spec.lo, spec.hi, pcts))
+    np.testing.assert_array_equal(pct_dev, o.percentiles_from_hist(to_np(res.hist), spec.lo, spec.hi, pcts))
+    np.testing.assert_array_equal(pct_dev, S.percentiles(res.hist, spec.lo, spec.hi, pcts))
 
 
 def test_histogram_outliers_and_narrow_range(api):
