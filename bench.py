@@ -223,11 +223,34 @@ def run_reference(args):
             "gpu_launches": 0,
             "note": "the reference ships no implementation of the 5-equation loop (SURVEY.md 0); this arm times the "
                     "in-repo C restatement (oracle/ufair_oracle.c) on the host cores"}
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 # ------------------------------------------------------------------------------------------------
+_REAL_STDOUT = None
+
+
+def claim_stdout():
+    """Keep stdout for the ONE JSON line: everything else any library prints to fd 1 (NCCL's version
+    banner, for one) is sent to stderr for the life of the process."""
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit(line):
+    data = (json.dumps(line) + "\n").encode()
+    if _REAL_STDOUT is None:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+    else:
+        os.write(_REAL_STDOUT, data)
+
+
 def main():
+    claim_stdout()
     args = parse()
     if args.impl == "reference":
         run_reference(args)
@@ -243,7 +266,6 @@ def main():
     torch.cuda.set_device(local)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        os.environ["NCCL_DEBUG"] = os.environ.get("UFAIR_NCCL_DEBUG", "WARN")  # keep stdout to the one JSON line
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     n_gpus = world
     L = _abi.lib()
@@ -408,7 +430,7 @@ def main():
         dist.barrier()
         dist.destroy_process_group()
     if rank == 0:
-        print(json.dumps(line), flush=True)
+        emit(line)
 
 
 if __name__ == "__main__":
