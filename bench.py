@@ -37,6 +37,19 @@ FLOPS_PER_STEP = 751.0               # 163 simple + 15 exp(28) + 3 log(36) + 3 s
 METRIC = "ensemble member-timesteps/sec"
 
 
+def algorithmic_flops(gas_form):
+    """SURVEY.md 8(d) convention (exp = 28, log = 36, sqrt = 10, div = 10 FP64 flops), per member-step,
+    for the pools and forcing terms the parameters actually use: per gas 18 + 8 n_pool simple flops,
+    1 + n_pool exponentials, one division, a log / sqrt where that term exists; 13 for the thermal
+    step.  Four pools and all three terms in every gas give the survey's 751."""
+    total = 13.0
+    for f in gas_form:
+        n_pool = (f & 7) or 4
+        terms = (f >> 4) & 7 or 7
+        total += 18 + 8 * n_pool + 28 * (1 + n_pool) + 10 + (36 if terms & 1 else 0) + (10 if terms & 4 else 0)
+    return total
+
+
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -52,6 +65,7 @@ def parse():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--sparse", action="store_true", help="literature-style sparse parameters (1-pool CH4/N2O)")
+    ap.add_argument("--general-kernel", action="store_true", help="experiment: never pick a specialised per-gas form")
     ap.add_argument("--no-stats", action="store_true", help="experiment: integrate without histogram/moments")
     ap.add_argument("--outputs", default="C,RF,T", help="experiment: comma list of outputs written to HBM ('' = none)")
     return ap.parse_args()
@@ -274,7 +288,11 @@ def main():
     E, gp, tp = device_ensemble(torch, M, n_t, rank, dense=not args.sparse)
     spec = None if args.no_stats else conc.HistSpec()
     outs = tuple(o for o in args.outputs.split(",") if o)
-    plan = conc.DevicePlan(E, gp, tp, stats=spec, precision=args.precision, outputs=outs)
+    plan = conc.DevicePlan(E, gp, tp, stats=spec, precision=args.precision, outputs=outs,
+                           gas_form=None if args.general_kernel else "auto")
+    vform, vgpl, vmw = plan.kernel_variant()
+    flops_step = algorithmic_flops(plan.gas_form if not args.general_kernel else (0,) * N_GAS)
+    assert args.sparse or flops_step == FLOPS_PER_STEP
     res = plan.result
     if args.precision == "f32":
         pass  # DevicePlan converted the inputs; E/gp/tp (f64) are only kept for the CPU sample
@@ -356,13 +374,13 @@ def main():
         fpeak_burst = rates[0]
         fpeak = statistics.median(rates[5:])
         bytes_per_launch = (N_GAS + 2 * N_GAS + 1) * es * float(M) * n_t
-        flops_per_launch = FLOPS_PER_STEP * float(M) * n_t
+        flops_per_launch = flops_step * float(M) * n_t
         a_hbm = bytes_per_launch / (kernel_ms * 1e-3) / 1e9
         a_fp = flops_per_launch / (kernel_ms * 1e-3) / 1e12
         traffic = None  # DRAM bytes per launch, scaled from the committed ncu --set full capture
         try:
             tj = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get(args.precision)
-            if tj and spec is not None and outs == ("C", "RF", "T"):
+            if tj and spec is not None and outs == ("C", "RF", "T") and not args.sparse:
                 traffic = tj["bytes_per_member_step"] * float(M) * n_t
         except Exception:
             pass
@@ -376,7 +394,8 @@ def main():
             "traffic": traffic, "kernel": "ufair_integrate_kernel<%s,3,EXP>" % ("double" if es == 8 else "float"),
             "kernel_ms": kernel_ms, "kernel_share_of_step": kernel_ms / ms_per_step,
             "algorithmic_bytes_per_member_step": (N_GAS + 2 * N_GAS + 1) * es,
-            "algorithmic_flops_per_member_step": FLOPS_PER_STEP,
+            "algorithmic_flops_per_member_step": flops_step,
+            "kernel_variant": {"form": list(vform), "gases_per_lane": vgpl, "members_per_warp": vmw},
             "hbm": {"achieved": a_hbm, "peak": hbm_peak, "unit": "GB/s", "frac": a_hbm / hbm_peak, "peak_source": hbm_src},
             bound: {"achieved": a_fp, "peak": fpeak, "unit": "TFLOP/s", "frac": a_fp / fpeak,
                     "peak_burst": fpeak_burst, "frac_of_burst": a_fp / fpeak_burst,

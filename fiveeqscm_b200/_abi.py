@@ -7,7 +7,7 @@ from __future__ import annotations
 import ctypes as C
 import os
 
-ABI_VERSION = 1
+ABI_VERSION = 2
 MAX_GAS = 4
 N_POOL = 4
 
@@ -15,6 +15,12 @@ N_POOL = 4
 GP_A0, GP_TAU0, GP_R0, GP_RU, GP_RT, GP_RA, GP_C0, GP_EMIS2CONC, GP_F1, GP_F2, GP_F3 = (
     0, 4, 8, 9, 10, 11, 12, 13, 14, 15, 16)
 GP_COUNT = 17
+TERM_LOG, TERM_LIN, TERM_SQRT = 1, 2, 4
+
+
+def form(n_pool: int, terms: int) -> int:
+    """UFAIR_FORM(n_pool, terms) of include/ufair.h."""
+    return (n_pool & 7) | ((terms & 7) << 4)
 TP_Q1, TP_Q2, TP_D1, TP_D2 = 0, 1, 2, 3
 TP_COUNT = 4
 
@@ -72,6 +78,8 @@ class UfairDesc(C.Structure):
         ("hist_rows", C.c_int32),
         ("hist_private", C.c_void_p),
         ("moments_private", C.c_void_p),
+        ("gas_form", C.c_uint8 * 4),
+        ("reserved1", C.c_uint32),
     ]
 
     def __init__(self, **kw):
@@ -104,6 +112,10 @@ SIGNATURES = {
     "ufair_block_members": (_i64, []),
     "ufair_run_f64": (C.c_int, [C.POINTER(UfairDesc), _vp]),
     "ufair_run_f32": (C.c_int, [C.POINTER(UfairDesc), _vp]),
+    "ufair_detect_form_f64": (C.c_int, [C.POINTER(UfairDesc), _vp, C.POINTER(C.c_uint8), _vp]),
+    "ufair_detect_form_f32": (C.c_int, [C.POINTER(UfairDesc), _vp, C.POINTER(C.c_uint8), _vp]),
+    "ufair_kernel_variant": (C.c_int, [C.POINTER(UfairDesc), _i32, C.POINTER(C.c_uint32), C.POINTER(_i32),
+                                       C.POINTER(_i32)]),
     "ufair_stats_reset": (C.c_int, [C.POINTER(UfairDesc), _vp]),
     "ufair_stats_moments_f64": (C.c_int, [C.POINTER(UfairDesc), _vp]),
     "ufair_stats_moments_f32": (C.c_int, [C.POINTER(UfairDesc), _vp]),

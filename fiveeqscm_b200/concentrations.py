@@ -124,7 +124,7 @@ def _round_up(n, m):
 
 
 def _build_desc(G, n_t, M, ld, n_scen, e_scen, fext_mode, alpha_mode, newton_iters, t_mode, outputs, dt, iirf_h,
-                iirf_max, stats: Optional[HistSpec]):
+                iirf_max, stats: Optional[HistSpec], gas_form=None):
     if alpha_mode not in _ALPHA:
         raise ValueError(f"alpha_mode must be one of {sorted(_ALPHA)}")
     if t_mode not in _TMODE:
@@ -143,13 +143,39 @@ def _build_desc(G, n_t, M, ld, n_scen, e_scen, fext_mode, alpha_mode, newton_ite
         d.hist_bins, d.hist_copies = int(stats.bins), int(stats.copies)
         d.hist_lo, d.hist_hi = float(stats.lo), float(stats.hi)
         d.hist_t0, d.hist_rows = 0, n_t
+    if gas_form is not None and not isinstance(gas_form, str):
+        if len(gas_form) != G:
+            raise ValueError("gas_form must have one entry per gas")
+        for g, f in enumerate(gas_form):
+            d.gas_form[g] = _form_byte(f)
     return d
+
+
+def _form_byte(f) -> int:
+    """One gas_form entry: None / 0 (unspecified), a raw UFAIR_FORM byte, or (n_pool, "log+lin+sqrt")."""
+    if f is None:
+        return 0
+    if isinstance(f, (int, np.integer)):
+        if not 0 <= int(f) <= 0x7f or (int(f) & 7) > 4:
+            raise ValueError(f"bad gas_form byte {f!r}")
+        return int(f)
+    n_pool, terms = f
+    if not 1 <= int(n_pool) <= 4:
+        raise ValueError("gas_form n_pool must be 1..4")
+    bits = {"log": _abi.TERM_LOG, "lin": _abi.TERM_LIN, "sqrt": _abi.TERM_SQRT}
+    t = 0
+    for name in (terms.split("+") if isinstance(terms, str) else terms):
+        if name not in bits:
+            raise ValueError(f"unknown forcing term {name!r}; choose from {sorted(bits)}")
+        t |= bits[name]
+    return _abi.form(int(n_pool), t)
 
 
 def run_ensemble(emissions, gas_params, thermal_params, *, dt=1.0, scen_idx=None, e_scale=None, f_ext=None,
                  fext_per_member=False, state_in=None, alpha_mode="exp", newton_iters=0, iirf_max=None,
                  iirf_h=100.0, t_mode="mid", outputs: Sequence[str] = ("C", "RF", "T"), stats: Optional[HistSpec] = None,
-                 precision="f64", return_state=True, chunk_members=65536, workspace=None, out=None) -> EnsembleResult:
+                 precision="f64", return_state=True, chunk_members=65536, workspace=None, out=None,
+                 gas_form="auto") -> EnsembleResult:
     """Integrate the 5-equation model for an ensemble (oxfair, .coveragerc:19, as one kernel launch).
 
     emissions      [G][n_t][M] per-member emission RATES, or [G][n_t][S] scenario-shared with
@@ -162,6 +188,11 @@ def run_ensemble(emissions, gas_params, thermal_params, *, dt=1.0, scen_idx=None
     alpha_mode     "exp" | "sinh" | "newton" (``newton_iters`` fixed steps) | "one".
     outputs        any of "C", "RF", "T", "alpha".   stats: HistSpec -> per-step T histogram + moments.
     precision      "f64" (default; <= 1e-10 relative vs the float64 oracle) or "f32" (<= 1e-4 K in T).
+    gas_form       per-gas specialisation (include/ufair.h UFAIR_FORM): "auto" scans the parameters on
+                   the device and lets the library skip pools with a_i == 0 and forcing terms whose
+                   coefficient is zero for every member (CUDA inputs; the host pipeline treats
+                   "auto" as None); None = no specialisation; or one entry per gas, e.g.
+                   [None, (1, "lin+sqrt"), (1, "lin+sqrt")] -- a promise the caller makes.
 
     torch.cuda tensors -> results are torch.cuda tensors (current stream, asynchronous);
     numpy / CPU tensors -> chunked host pipeline, results are numpy arrays.  For repeated host
@@ -175,10 +206,10 @@ def run_ensemble(emissions, gas_params, thermal_params, *, dt=1.0, scen_idx=None
     if on_device:
         return _run_device(torch, emissions, gas_params, thermal_params, dt, scen_idx, e_scale, f_ext,
                            fext_per_member, state_in, alpha_mode, newton_iters, iirf_max, iirf_h, t_mode,
-                           tuple(outputs), stats, precision, return_state)
+                           tuple(outputs), stats, precision, return_state, gas_form)
     return _run_host(torch, emissions, gas_params, thermal_params, dt, scen_idx, e_scale, f_ext, fext_per_member,
                      state_in, alpha_mode, newton_iters, iirf_max, iirf_h, t_mode, tuple(outputs), stats, precision,
-                     return_state, chunk_members, workspace, out)
+                     return_state, chunk_members, workspace, out, gas_form)
 
 
 def _shapes(E_shape, gp_shape, tp_shape, scen_idx, fext_shape, fext_per_member):
@@ -218,7 +249,7 @@ class DevicePlan:
 
     def __init__(self, E, gp, tp, *, dt=1.0, scen_idx=None, e_scale=None, f_ext=None, fext_per_member=False,
                  state_in=None, alpha_mode="exp", newton_iters=0, iirf_max=None, iirf_h=100.0, t_mode="mid",
-                 outputs=("C", "RF", "T"), stats=None, precision="f64", return_state=True):
+                 outputs=("C", "RF", "T"), stats=None, precision="f64", return_state=True, gas_form="auto"):
         torch = _require_cuda()
         self._L = _abi.lib()
         dtype = torch.float64 if precision == "f64" else torch.float32
@@ -252,7 +283,7 @@ class DevicePlan:
         gp_d, tp_d = member_rows(gp, "gas_params"), member_rows(tp, "thermal_params")
         keep += [E_d, gp_d, tp_d]
         d = _build_desc(G, n_t, M, ld, n_scen, e_scen, fext_mode, alpha_mode, newton_iters, t_mode, outputs, dt,
-                        iirf_h, iirf_max, stats)
+                        iirf_h, iirf_max, stats, gas_form)
         d.emissions, d.gas_params, d.thermal_params = E_d.data_ptr(), gp_d.data_ptr(), tp_d.data_ptr()
         if scen_idx is not None:
             si = torch.as_tensor(scen_idx, device=dev).to(torch.int32).contiguous()
@@ -304,9 +335,28 @@ class DevicePlan:
         res._keep = keep  # inputs stay alive as long as the result does
         self.desc, self.result, self._keep = d, res, keep
         self._run = self._L.ufair_run_f64 if precision == "f64" else self._L.ufair_run_f32
+        if isinstance(gas_form, str):
+            if gas_form != "auto":
+                raise ValueError("gas_form must be 'auto', None or one entry per gas")
+            if M:  # one scan of the parameter arrays (synchronises the current stream once, at plan time)
+                scratch = torch.empty(_abi.MAX_GAS, dtype=torch.int32, device=dev)
+                form = (C.c_uint8 * _abi.MAX_GAS)()
+                detect = self._L.ufair_detect_form_f64 if precision == "f64" else self._L.ufair_detect_form_f32
+                with torch.cuda.device(dev):
+                    _abi.check(detect(C.byref(d), scratch.data_ptr(), form, self._stream()))
+                for g in range(G):
+                    d.gas_form[g] = form[g]
+        self.gas_form = tuple(int(d.gas_form[g]) for g in range(G))
 
     def _stream(self):
         return _torch().cuda.current_stream(self.device).cuda_stream
+
+    def kernel_variant(self):
+        """(form, gases_per_lane, members_per_warp) of the integrator variant this plan launches;
+        form is one UFAIR_FORM byte per gas, 0 everywhere = the general kernel."""
+        f, g, mw = C.c_uint32(), C.c_int32(), C.c_int32()
+        _abi.check(self._L.ufair_kernel_variant(C.byref(self.desc), 8 if self.precision == "f64" else 4, f, g, mw))
+        return tuple((f.value >> (8 * k)) & 0xff for k in range(self.n_gas)), g.value, mw.value
 
     def reset_stats(self):
         if self.stats is not None:
@@ -338,11 +388,11 @@ class DevicePlan:
 
 
 def _run_device(torch, E, gp, tp, dt, scen_idx, e_scale, f_ext, fext_per_member, state_in, alpha_mode, newton_iters,
-                iirf_max, iirf_h, t_mode, outputs, stats, precision, return_state):
+                iirf_max, iirf_h, t_mode, outputs, stats, precision, return_state, gas_form="auto"):
     return DevicePlan(E, gp, tp, dt=dt, scen_idx=scen_idx, e_scale=e_scale, f_ext=f_ext,
                       fext_per_member=fext_per_member, state_in=state_in, alpha_mode=alpha_mode,
                       newton_iters=newton_iters, iirf_max=iirf_max, iirf_h=iirf_h, t_mode=t_mode, outputs=outputs,
-                      stats=stats, precision=precision, return_state=return_state).run()
+                      stats=stats, precision=precision, return_state=return_state, gas_form=gas_form).run()
 
 
 class Workspace:
@@ -365,7 +415,8 @@ class Workspace:
 
 
 def _run_host(torch, E, gp, tp, dt, scen_idx, e_scale, f_ext, fext_per_member, state_in, alpha_mode, newton_iters,
-              iirf_max, iirf_h, t_mode, outputs, stats, precision, return_state, chunk_members, workspace, out=None):
+              iirf_max, iirf_h, t_mode, outputs, stats, precision, return_state, chunk_members, workspace, out=None,
+              gas_form=None):
     L = _abi.lib()
     npdt = np.float64 if precision == "f64" else np.float32
 
@@ -380,7 +431,7 @@ def _run_host(torch, E, gp, tp, dt, scen_idx, e_scale, f_ext, fext_per_member, s
     fshape = None if f_ext is None else f_ext.shape
     G, n_t, M, e_scen, n_scen, fext_mode = _shapes(E.shape, gp.shape, tp.shape, scen_idx, fshape, fext_per_member)
     d = _build_desc(G, n_t, M, M, n_scen, e_scen, fext_mode, alpha_mode, newton_iters, t_mode, outputs, dt, iirf_h,
-                    iirf_max, stats)
+                    iirf_max, stats, gas_form)
     d.emissions, d.gas_params, d.thermal_params = E.ctypes.data, gp.ctypes.data, tp.ctypes.data
     keep = [E, gp, tp]
     if scen_idx is not None:

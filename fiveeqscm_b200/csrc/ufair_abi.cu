@@ -130,16 +130,16 @@ static EncodeTiledFn encode_tiled() {
 
 // emissions [n_gas][n_t][ld] -> rank-3 map, box = MW members x kTT steps x n_gas gases;
 // f_ext [n_t][ld] -> rank-2 map, box = MW x kTT.  Out-of-range parts of a box are zero-filled.
-template <typename Real> static int make_tensor_maps(const ufair_desc* d, CUtensorMap* tmE, CUtensorMap* tmF) {
+int make_tensor_maps(const ufair_desc* d, size_t elem, int mw_members, CUtensorMap* tmE, CUtensorMap* tmF) {
   memset(tmE, 0, sizeof(*tmE));
   memset(tmF, 0, sizeof(*tmF));
   const bool e_member = d->e_mode == UFAIR_E_MEMBER, f_member = d->fext_mode == UFAIR_FEXT_MEMBER;
   if (!e_member && !f_member) return UFAIR_OK;
   EncodeTiledFn enc = encode_tiled();
   if (!enc) return set_error(UFAIR_ERR_CUDA, "cuTensorMapEncodeTiled is not available from this driver");
-  const CUtensorMapDataType dt = sizeof(Real) == 8 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT64 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32;
-  const cuuint32_t mw = (cuuint32_t)members_per_warp(sizeof(Real), d->n_gas);
-  const cuuint64_t row = (cuuint64_t)d->ld_member * sizeof(Real);
+  const CUtensorMapDataType dt = elem == 8 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT64 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32;
+  const cuuint32_t mw = (cuuint32_t)mw_members;
+  const cuuint64_t row = (cuuint64_t)d->ld_member * elem;
   const cuuint32_t ones[3] = {1, 1, 1};
   if (e_member) {
     const cuuint64_t dims[3] = {(cuuint64_t)d->ld_member, (cuuint64_t)d->n_t, (cuuint64_t)d->n_gas};
@@ -161,13 +161,12 @@ template <typename Real> static int make_tensor_maps(const ufair_desc* d, CUtens
 }
 
 template <typename Real, int NGAS>
-static cudaError_t dispatch_mode(const KArgs<Real>& a, const CUtensorMap& tmE, const CUtensorMap& tmF, int mode,
-                                 cudaStream_t s) {
-  switch (mode) {
-    case UFAIR_ALPHA_EXP: return launch_integrate<Real, NGAS, UFAIR_ALPHA_EXP>(a, tmE, tmF, s);
-    case UFAIR_ALPHA_SINH: return launch_integrate<Real, NGAS, UFAIR_ALPHA_SINH>(a, tmE, tmF, s);
-    case UFAIR_ALPHA_NEWTON: return launch_integrate<Real, NGAS, UFAIR_ALPHA_NEWTON>(a, tmE, tmF, s);
-    default: return launch_integrate<Real, NGAS, UFAIR_ALPHA_ONE>(a, tmE, tmF, s);
+static int dispatch_mode(const ufair_desc* d, const KArgs<Real>& a, cudaStream_t s) {
+  switch (d->alpha_mode) {
+    case UFAIR_ALPHA_EXP: return launch_integrate<Real, NGAS, UFAIR_ALPHA_EXP>(d, a, s);
+    case UFAIR_ALPHA_SINH: return launch_integrate<Real, NGAS, UFAIR_ALPHA_SINH>(d, a, s);
+    case UFAIR_ALPHA_NEWTON: return launch_integrate<Real, NGAS, UFAIR_ALPHA_NEWTON>(d, a, s);
+    default: return launch_integrate<Real, NGAS, UFAIR_ALPHA_ONE>(d, a, s);
   }
 }
 
@@ -227,18 +226,58 @@ template <typename Real> int run_device(const ufair_desc* d, cudaStream_t stream
   int rc = validate_desc(d, sizeof(Real));
   if (rc != UFAIR_OK) return rc;
   if (d->n_member == 0 || d->n_t == 0) return UFAIR_OK;
-  KArgs<Real> a = make_args<Real>(d);
-  CUtensorMap tmE, tmF;
-  rc = make_tensor_maps<Real>(d, &tmE, &tmF);
-  if (rc != UFAIR_OK) return rc;
-  cudaError_t e;
+  const KArgs<Real> a = make_args<Real>(d);
   switch (d->n_gas) {
-    case 1: e = dispatch_mode<Real, 1>(a, tmE, tmF, d->alpha_mode, stream); break;
-    case 2: e = dispatch_mode<Real, 2>(a, tmE, tmF, d->alpha_mode, stream); break;
-    case 3: e = dispatch_mode<Real, 3>(a, tmE, tmF, d->alpha_mode, stream); break;
-    default: e = dispatch_mode<Real, 4>(a, tmE, tmF, d->alpha_mode, stream); break;
+    case 1: return dispatch_mode<Real, 1>(d, a, stream);
+    case 2: return dispatch_mode<Real, 2>(d, a, stream);
+    case 3: return dispatch_mode<Real, 3>(d, a, stream);
+    default: return dispatch_mode<Real, 4>(d, a, stream);
   }
-  if (e != cudaSuccess) return cuda_error(e, "ufair_integrate_kernel launch");
+}
+
+// ---- gas_form detection: which pools carry mass, which forcing terms exist, over all members -------
+// flags[g]: bit q (q = 1..3) pool q+1 in use (a != 0 or initial state != 0); bits 4..6 f1 / f2 / f3 != 0
+template <typename Real>
+__global__ void detect_form_kernel(const Real* gp, const Real* state_in, int n_gas, long long n_member, long long ld,
+                                   int* flags) {
+  const int g = blockIdx.y;
+  int f = 0;
+  for (long long m = (long long)blockIdx.x * blockDim.x + threadIdx.x; m < n_member; m += (long long)gridDim.x * blockDim.x) {
+    const Real* p = gp + (long long)g * UFAIR_GP_COUNT * ld + m;
+    for (int q = 1; q < 4; ++q) {
+      if (p[(UFAIR_GP_A0 + q) * ld] != Real(0)) f |= 1 << q;
+      if (state_in && state_in[(long long)(5 * g + q) * ld + m] != Real(0)) f |= 1 << q;
+    }
+    if (p[UFAIR_GP_F1 * ld] != Real(0)) f |= 16;
+    if (p[UFAIR_GP_F2 * ld] != Real(0)) f |= 32;
+    if (p[UFAIR_GP_F3 * ld] != Real(0)) f |= 64;
+  }
+  f = __reduce_or_sync(0xffffffffu, f);
+  if ((threadIdx.x & 31) == 0 && f) atomicOr(flags + g, f);
+}
+
+template <typename Real> int detect_form(const ufair_desc* d, int32_t* scratch, uint8_t* form, cudaStream_t stream) {
+  int rc = validate_desc(d, sizeof(Real));
+  if (rc != UFAIR_OK) return rc;
+  if (!scratch || !form) return set_error(UFAIR_ERR_ARG, "ufair_detect_form: scratch / form must not be NULL");
+  for (int g = 0; g < d->n_gas; ++g) form[g] = UFAIR_FORM(1, UFAIR_TERM_LIN);  // no members: nothing is used
+  if (d->n_member == 0) return UFAIR_OK;
+  cudaError_t e = cudaMemsetAsync(scratch, 0, UFAIR_MAX_GAS * sizeof(int32_t), stream);
+  if (e != cudaSuccess) return cuda_error(e, "cudaMemsetAsync(scratch)");
+  const unsigned bx = (unsigned)((d->n_member + 255) / 256 < 592 ? (d->n_member + 255) / 256 : 592);
+  detect_form_kernel<Real><<<dim3(bx, (unsigned)d->n_gas), 256, 0, stream>>>(
+      (const Real*)d->gas_params, (const Real*)d->state_in, d->n_gas, d->n_member, d->ld_member, scratch);
+  if ((e = cudaGetLastError()) != cudaSuccess) return cuda_error(e, "detect_form_kernel launch");
+  int32_t flags[UFAIR_MAX_GAS];
+  if ((e = cudaMemcpyAsync(flags, scratch, sizeof(flags), cudaMemcpyDeviceToHost, stream)) != cudaSuccess)
+    return cuda_error(e, "cudaMemcpyAsync(flags)");
+  if ((e = cudaStreamSynchronize(stream)) != cudaSuccess) return cuda_error(e, "cudaStreamSynchronize");
+  for (int g = 0; g < d->n_gas; ++g) {
+    const int n_pool = (flags[g] & 8) ? 4 : (flags[g] & 4) ? 3 : (flags[g] & 2) ? 2 : 1;
+    int terms = (flags[g] >> 4) & 7;
+    if (terms == 0) terms = UFAIR_TERM_LIN;  // no forcing at all: the linear term (with f2 == 0) is the cheapest
+    form[g] = UFAIR_FORM(n_pool, terms);
+  }
   return UFAIR_OK;
 }
 
@@ -458,6 +497,25 @@ int ufair_run_f32(const ufair_desc* d, void* stream) { return run_device<float>(
 
 int ufair_stats_moments_f64(const ufair_desc* d, void* stream) { return run_moments<double>(d, (cudaStream_t)stream); }
 int ufair_stats_moments_f32(const ufair_desc* d, void* stream) { return run_moments<float>(d, (cudaStream_t)stream); }
+
+int ufair_detect_form_f64(const ufair_desc* d, int32_t* scratch, uint8_t* form, void* stream) {
+  return detect_form<double>(d, scratch, form, (cudaStream_t)stream);
+}
+int ufair_detect_form_f32(const ufair_desc* d, int32_t* scratch, uint8_t* form, void* stream) {
+  return detect_form<float>(d, scratch, form, (cudaStream_t)stream);
+}
+
+int ufair_kernel_variant(const ufair_desc* d, int32_t elem_size, uint32_t* form, int32_t* gpl, int32_t* mw) {
+  if (elem_size != 8 && elem_size != 4) return set_error(UFAIR_ERR_ARG, "elem_size must be 8 or 4");
+  const int rc = validate_desc(d, (size_t)elem_size);
+  if (rc != UFAIR_OK) return rc;
+  const unsigned f = pick_form(d);
+  const int g = gases_per_lane(elem_size, d->n_gas, f);
+  if (form) *form = f;
+  if (gpl) *gpl = g;
+  if (mw) *mw = members_per_warp(elem_size, d->n_gas, g);
+  return UFAIR_OK;
+}
 
 int ufair_stats_reset(const ufair_desc* d, void* stream) {
   int rc = check_stats_desc(d);

@@ -1,7 +1,8 @@
-// explicit instantiations of the fused integrator: float, 2 gas(es), all alpha modes
+// explicit instantiations of the fused integrator: float, 2 gas(es), all alpha modes, and the
+// specialised per-gas forms of the default (EXP) mode
 #include "ufair_kernel.cuh"
 namespace ufair {
-UFAIR_DEFINE_LAUNCH(float, 2, UFAIR_ALPHA_EXP)
+UFAIR_DEFINE_LAUNCH_EXP(float, 2, UFAIR_TRY_FORM(float, 2, kForms2[0]))
 UFAIR_DEFINE_LAUNCH(float, 2, UFAIR_ALPHA_SINH)
 UFAIR_DEFINE_LAUNCH(float, 2, UFAIR_ALPHA_NEWTON)
 UFAIR_DEFINE_LAUNCH(float, 2, UFAIR_ALPHA_ONE)

@@ -61,11 +61,17 @@
 #ifndef UFAIR_WARPS
 #define UFAIR_WARPS 1  // warps per CTA.  A CTA is only a launch / shared-memory grouping (warps never
 #endif                 // synchronise); single-warp CTAs measured ~2 % faster than 4 (finer refill)
-#ifndef UFAIR_MINB_F64  // resident WARPS per SM the register allocator must allow (CTAs = this / WARPS)
-#define UFAIR_MINB_F64 ((UFAIR_GPL_ALL_F64 ? 12 : 20) / UFAIR_WARPS)
+#ifndef UFAIR_MINB_F64  // resident CTAs per SM the register allocator must allow, one gas per lane
+#define UFAIR_MINB_F64 (20 / UFAIR_WARPS)
 #endif
 #ifndef UFAIR_MINB_F32
-#define UFAIR_MINB_F32 ((UFAIR_GPL_ALL_F32 ? 16 : 32) / UFAIR_WARPS)
+#define UFAIR_MINB_F32 (32 / UFAIR_WARPS)
+#endif
+#ifndef UFAIR_MINB_F64_FORM  // resident WARPS per SM for the specialised (per-gas form) kernels
+#define UFAIR_MINB_F64_FORM 12
+#endif
+#ifndef UFAIR_MINB_F32_FORM
+#define UFAIR_MINB_F32_FORM 16
 #endif
 #ifndef UFAIR_TT
 #define UFAIR_TT 8  // time steps per shared-memory tile (8 measured ~2 % faster than 4)
@@ -77,13 +83,49 @@ constexpr int kWarps = UFAIR_WARPS;
 constexpr int kTT = UFAIR_TT;
 constexpr int kStages = 2;  // tile ring depth
 
-constexpr int gases_per_lane(int elem_size, int n_gas) {
-  return (elem_size == 8 ? UFAIR_GPL_ALL_F64 : UFAIR_GPL_ALL_F32) ? n_gas : 1;
+// ---- per-gas specialisation ("form"): 8 bits per gas, the descriptor's gas_form byte ------------
+// bits 0-2: pools in use (0 = all four), bits 4-6: forcing terms present (0 = all three).  A form is
+// the caller's promise that the other pools have a_i = 0 and zero initial state and that the other
+// forcing coefficients are zero for every member; the specialised kernels then never touch them.
+// Results are those of the dense kernel (adding exact zeros), only cheaper.
+constexpr unsigned form_byte(int n_pool, unsigned terms) { return (unsigned)n_pool | (terms << 4); }
+constexpr unsigned kGasFull = 0u;
+constexpr unsigned kGasOneSqrt = form_byte(1, UFAIR_TERM_LIN | UFAIR_TERM_SQRT);  // CH4 / N2O-like
+constexpr unsigned kGasOneLin = form_byte(1, UFAIR_TERM_LIN);                     // HFC-like
+constexpr unsigned pack_form(unsigned g0, unsigned g1 = 0, unsigned g2 = 0, unsigned g3 = 0) {
+  return g0 | (g1 << 8) | (g2 << 16) | (g3 << 24);
+}
+__host__ __device__ constexpr int form_pools(unsigned form, int g) {
+  const int n = (int)((form >> (8 * g)) & 7u);
+  return n ? n : 4;
+}
+__host__ __device__ constexpr unsigned form_terms(unsigned form, int g) {
+  const unsigned t = (form >> (8 * g + 4)) & 7u;
+  return t ? t : 7u;
+}
+// does the instantiated form `have` do everything the requested form `want` needs?
+inline bool form_covers(unsigned have, unsigned want, int n_gas) {
+  for (int g = 0; g < n_gas; ++g)
+    if (form_pools(have, g) < form_pools(want, g) || (form_terms(have, g) & form_terms(want, g)) != form_terms(want, g))
+      return false;
+  return true;
+}
+// the specialised forms that are instantiated (alpha mode EXP only), most specific first
+constexpr unsigned kForms1[] = {pack_form(kGasOneLin), pack_form(kGasOneSqrt)};
+constexpr unsigned kForms2[] = {pack_form(kGasFull, kGasOneSqrt)};
+constexpr unsigned kForms3[] = {pack_form(kGasFull, kGasOneSqrt, kGasOneSqrt)};
+constexpr unsigned kForms4[] = {pack_form(kGasFull, kGasOneSqrt, kGasOneSqrt, kGasOneLin)};
+
+// gases a lane integrates: the dense kernels follow the UFAIR_GPL_ALL_* switches, a specialised
+// form always keeps a member's gases in one lane (the per-gas code differs, so it cannot share a warp
+// instruction stream across gases)
+constexpr int gases_per_lane(int elem_size, int n_gas, unsigned form = 0) {
+  return (form != 0 || (elem_size == 8 ? UFAIR_GPL_ALL_F64 : UFAIR_GPL_ALL_F32)) ? n_gas : 1;
 }
 // members per warp: rows of MW elements must be a multiple of 16 bytes for the TMA box
-constexpr int members_per_warp(int elem_size, int n_gas) {
-  const int q = 16 / elem_size;                                    // elements per 16 bytes
-  const int groups = n_gas / gases_per_lane(elem_size, n_gas);     // lanes per member
+constexpr int members_per_warp(int elem_size, int n_gas, int gpl) {
+  const int q = 16 / elem_size;    // elements per 16 bytes
+  const int groups = n_gas / gpl;  // lanes per member
   return (32 / groups) / q * q;
 }
 
@@ -186,10 +228,10 @@ constexpr int extra_rows(int amode) { return amode == UFAIR_ALPHA_NEWTON ? 3 : (
 constexpr size_t round128(size_t b) { return (b + 127) / 128 * 128; }
 
 // per-WARP shared memory, in bytes (every piece 128-byte aligned: tensor-map TMA destinations)
-template <typename Real, int NGAS, int AMODE> struct WarpSmem {
-  static constexpr int GPL = gases_per_lane(sizeof(Real), NGAS);
-  static constexpr bool HOT_SMEM = (GPL == 1);
-  static constexpr int MW = members_per_warp(sizeof(Real), NGAS);
+template <typename Real, int NGAS, int AMODE, int GPL_> struct WarpSmem {
+  static constexpr int GPL = GPL_;
+  static constexpr bool HOT_SMEM = (GPL == 1) || sizeof(Real) == 8;
+  static constexpr int MW = members_per_warp(sizeof(Real), NGAS, GPL);
   static constexpr int G_HOT = G_COLD;                            // first hot row (if in smem)
   static constexpr int G_X0 = G_COLD + (HOT_SMEM ? H_COUNT : 0);  // SINH: g0; NEWTON: g1, ln g0, 1/c
   static constexpr int PG = G_X0 + extra_rows(AMODE);             // rows per gas
@@ -209,15 +251,30 @@ template <typename Real, int NGAS, int AMODE> struct WarpSmem {
   static __host__ __device__ constexpr uint32_t bytes(bool fx_member) { return off_bar(fx_member) + 128u; }
 };
 
-constexpr int min_blocks(int elem_size) { return elem_size == 8 ? UFAIR_MINB_F64 : UFAIR_MINB_F32; }
+// resident CTAs per SM the register allocator must allow
+constexpr int min_blocks(int elem_size, int n_gas, int gpl, unsigned form) {
+  if (form != 0) return (elem_size == 8 ? UFAIR_MINB_F64_FORM : UFAIR_MINB_F32_FORM) / UFAIR_WARPS;
+  if (elem_size == 4) return gpl == n_gas ? 16 / UFAIR_WARPS : UFAIR_MINB_F32;
+  return (gpl == n_gas && n_gas > 1) ? 12 / UFAIR_WARPS : UFAIR_MINB_F64;
+}
 
 // EMEM: per-member emissions (TMA-staged tile) vs scenario-shared (read-only path + register prefetch)
-template <typename Real, int NGAS, int AMODE, bool EMEM>
-__global__ void __launch_bounds__(kWarps * 32, min_blocks(sizeof(Real)))
+// pool sum in the dense kernel's association, (R1 + R2) + (R3 + R4), without the absent pools
+template <typename Real> __device__ __forceinline__ Real sum_pools(const Real (&R)[4], int np) {
+  if (np >= 4) return (R[0] + R[1]) + (R[2] + R[3]);
+  if (np == 3) return (R[0] + R[1]) + R[2];
+  if (np == 2) return R[0] + R[1];
+  return R[0];
+}
+
+// GPL: gases per lane (1 or NGAS); FORM: per-gas specialisation (0 = dense; needs GPL == NGAS)
+template <typename Real, int NGAS, int AMODE, bool EMEM, int GPL_, unsigned FORM>
+__global__ void __launch_bounds__(kWarps * 32, min_blocks(sizeof(Real), NGAS, GPL_, FORM))
     ufair_integrate_kernel(const __grid_constant__ KArgs<Real> a, const __grid_constant__ CUtensorMap tmE,
                            const __grid_constant__ CUtensorMap tmF) {
+  static_assert(FORM == 0 || GPL_ == NGAS, "a per-gas form needs all gases of a member in one lane");
   using M = Math<Real>;
-  using WS = WarpSmem<Real, NGAS, AMODE>;
+  using WS = WarpSmem<Real, NGAS, AMODE, GPL_>;
   constexpr int GPL = WS::GPL;           // gases this lane integrates
   constexpr int GROUPS = NGAS / GPL;     // lanes per member
   constexpr int MW = WS::MW;             // members per warp
@@ -284,22 +341,26 @@ __global__ void __launch_bounds__(kWarps * 32, min_blocks(sizeof(Real)))
 #pragma unroll
   for (int gl = 0; gl < GPL; ++gl) {
     const int g = g0 + gl;
+    const int NP = form_pools(FORM, gl);         // pools this gas uses (4 unless specialised)
+    const unsigned TERMS = form_terms(FORM, gl);  // forcing terms this gas has
     const Real* p = a.gp + (long long)g * UFAIR_GP_COUNT * ld + m;
     double av[4], tau[4];
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
-      av[q] = (double)p[(UFAIR_GP_A0 + q) * ld];
-      tau[q] = (double)p[(UFAIR_GP_TAU0 + q) * ld];
+      av[q] = (q < NP) ? (double)p[(UFAIR_GP_A0 + q) * ld] : 0.0;
+      tau[q] = (q < NP) ? (double)p[(UFAIR_GP_TAU0 + q) * ld] : 1.0;
     }
     const double r0 = p[UFAIR_GP_R0 * ld], rU = p[UFAIR_GP_RU * ld], rT = p[UFAIR_GP_RT * ld], rA = p[UFAIR_GP_RA * ld];
     const double C0d = p[UFAIR_GP_C0 * ld], c = p[UFAIR_GP_EMIS2CONC * ld];
     double g1 = 0.0, sden = 0.0;
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
-      const double z = a.h / tau[q];
-      const double ez = exp(-z);
-      g1 += av[q] * tau[q] * (1.0 - (1.0 + z) * ez);
-      sden += av[q] * tau[q] * (1.0 - ez);
+      if (q < NP) {
+        const double z = a.h / tau[q];
+        const double ez = exp(-z);
+        g1 += av[q] * tau[q] * (1.0 - (1.0 + z) * ez);
+        sden += av[q] * tau[q] * (1.0 - ez);
+      }
     }
     const double sarg = sden / g1;
     const double inv_g1 = 1.0 / g1, invc = 1.0 / c;
@@ -307,8 +368,10 @@ __global__ void __launch_bounds__(kWarps * 32, min_blocks(sizeof(Real)))
     const double fold = (AMODE == UFAIR_ALPHA_SINH) ? 0.0 : lng0;
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
-      SETG(gl, G_KA0 + q, c * av[q] * tau[q]);
-      SETG(gl, G_K0 + q, (AMODE == UFAIR_ALPHA_ONE) ? -expm1(-a.dt / tau[q]) : a.dt / tau[q]);
+      if (q < NP) {
+        SETG(gl, G_KA0 + q, c * av[q] * tau[q]);
+        SETG(gl, G_K0 + q, (AMODE == UFAIR_ALPHA_ONE) ? -expm1(-a.dt / tau[q]) : a.dt / tau[q]);
+      }
     }
     const double hv[H_COUNT] = {r0 * inv_g1 + fold, rU * inv_g1, (rA - rU) * inv_g1 * invc, rT * inv_g1,
                                 a.clamp ? (a.iirf_max * inv_g1 + fold) : (double)INFINITY};
@@ -332,17 +395,17 @@ __global__ void __launch_bounds__(kWarps * 32, min_blocks(sizeof(Real)))
     }
     // a zero forcing coefficient means a zero term; the log / sqrt is skipped only when no lane of
     // the warp needs it (voted once, outside the loop; with all gases in one lane this is per gas)
-    need_log[gl] = __any_sync(FULL, f1v != Real(0));
-    need_sqrt[gl] = __any_sync(FULL, f3v != Real(0));
+    need_log[gl] = (TERMS & UFAIR_TERM_LOG) && __any_sync(FULL, f1v != Real(0));
+    need_sqrt[gl] = (TERMS & UFAIR_TERM_SQRT) && __any_sync(FULL, f3v != Real(0));
     mk1[gl] = (f1v != Real(0)) ? 0xffffffffu : 0u;
     mk3[gl] = (f3v != Real(0)) ? 0xffffffffu : 0u;
     pin(mk1[gl]);
     pin(mk3[gl]);
     const Real* si = a.state_in;
 #pragma unroll
-    for (int q = 0; q < 4; ++q) R[gl][q] = si ? si[(long long)(5 * g + q) * ld + m] : Real(0);
+    for (int q = 0; q < 4; ++q) R[gl][q] = (si && q < NP) ? si[(long long)(5 * g + q) * ld + m] : Real(0);
     Gcum[gl] = si ? si[(long long)(5 * g + 4) * ld + m] : Real(0);
-    sumR[gl] = (R[gl][0] + R[gl][1]) + (R[gl][2] + R[gl][3]);
+    sumR[gl] = sum_pools(R[gl], NP);
   }
   Real S0, S1, Tprev;
   {
@@ -411,6 +474,8 @@ __global__ void __launch_bounds__(kWarps * 32, min_blocks(sizeof(Real)))
     Real Fsum = 0;
 #pragma unroll
     for (int gl = 0; gl < GPL; ++gl) {
+      const int NP = form_pools(FORM, gl);
+      const unsigned TERMS = form_terms(FORM, gl);
       Real e;
       if (EMEM) {
         e = lds(e_addr + tt_off + (uint32_t)gl * GROW, Real());
@@ -441,7 +506,7 @@ __global__ void __launch_bounds__(kWarps * 32, min_blocks(sizeof(Real)))
             const Real ia = M::rcp(alpha);
             Real f = -iirf, fp = 0;
 #pragma unroll
-            for (int q = 0; q < 4; ++q) {
+            for (int q = 0; q < NP; ++q) {
               const Real z = PARG(gl, G_K0 + q) * hdt * ia;
               const Real mz = M::decay(z);
               const Real at = PARG(gl, G_KA0 + q) * invc;  // a_i tau_i
@@ -459,16 +524,17 @@ __global__ void __launch_bounds__(kWarps * 32, min_blocks(sizeof(Real)))
       Real mq[4];
 #pragma unroll
       for (int q = 0; q < 4; ++q)
-        mq[q] = (AMODE == UFAIR_ALPHA_ONE) ? PARG(gl, G_K0 + q) : M::decay(PARG(gl, G_K0 + q) * inva);
+        if (q < NP) mq[q] = (AMODE == UFAIR_ALPHA_ONE) ? PARG(gl, G_K0 + q) : M::decay(PARG(gl, G_K0 + q) * inva);
 #pragma unroll
-      for (int q = 0; q < 4; ++q) R[gl][q] = fma(mq[q], fma(ea, PARG(gl, G_KA0 + q), -R[gl][q]), R[gl][q]);
+      for (int q = 0; q < 4; ++q)
+        if (q < NP) R[gl][q] = fma(mq[q], fma(ea, PARG(gl, G_KA0 + q), -R[gl][q]), R[gl][q]);
       Gcum[gl] = fma(e, dt, Gcum[gl]);
-      sumR[gl] = (R[gl][0] + R[gl][1]) + (R[gl][2] + R[gl][3]);
+      sumR[gl] = sum_pools(R[gl], NP);
       const Real C = PARG(gl, G_C0) + sumR[gl];
       // ---- step_forc
       // (the log / sqrt VALUE is masked, not the product, so that a zero coefficient with an
       // infinite or NaN function value -- C0 = 0 gases -- still contributes exactly zero)
-      Real F = PARG(gl, G_F2) * sumR[gl];
+      Real F = (TERMS & UFAIR_TERM_LIN) ? PARG(gl, G_F2) * sumR[gl] : Real(0);
       if (need_log[gl]) F = fma(PARG(gl, G_F1), M::mask(M::log_(C * PARG(gl, G_INVC0)), mk1[gl]), F);
       if (need_sqrt[gl]) F = fma(PARG(gl, G_F3), M::mask(M::sqrt_(C) - PARG(gl, G_SQRTC0), mk3[gl]), F);
       if (wm & UFAIR_OUT_C) st_stream(pC + gl * gstride, C);
@@ -606,24 +672,65 @@ __global__ void __launch_bounds__(kWarps * 32, min_blocks(sizeof(Real)))
 #undef SETT
 }
 
-// one launcher per (Real, NGAS, AMODE); defined in ufair_inst_*.cu
-template <typename Real, int NGAS, int AMODE>
-cudaError_t launch_integrate(const KArgs<Real>& a, const CUtensorMap& tmE, const CUtensorMap& tmF, cudaStream_t stream);
+// ---- launchers: one per (Real, NGAS, AMODE), defined in ufair_inst_*.cu ----------------------------
+int make_tensor_maps(const ufair_desc* d, size_t elem, int mw_members, CUtensorMap* tmE, CUtensorMap* tmF);
+int cuda_error(cudaError_t e, const char* what);
 
-#define UFAIR_DEFINE_LAUNCH(Real, NGAS, AMODE)                                                                     \
-  template <>                                                                                                      \
-  cudaError_t launch_integrate<Real, NGAS, AMODE>(const KArgs<Real>& a, const CUtensorMap& tmE,                    \
-                                                  const CUtensorMap& tmF, cudaStream_t stream) {                   \
-    using WS = WarpSmem<Real, NGAS, AMODE>;                                                                        \
-    const size_t smem = (size_t)WS::bytes(a.fext_mode == UFAIR_FEXT_MEMBER) * kWarps;                                                                      \
-    auto kern = (a.e_mode == UFAIR_E_MEMBER) ? ufair_integrate_kernel<Real, NGAS, AMODE, true>                     \
-                                              : ufair_integrate_kernel<Real, NGAS, AMODE, false>;                  \
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);            \
-    if (e != cudaSuccess) return e;                                                                                \
-    const long long n_warp = (a.n_member + WS::MW - 1) / WS::MW;                                                   \
-    const unsigned grid = (unsigned)((n_warp + kWarps - 1) / kWarps);                                              \
-    kern<<<grid, kWarps * 32, smem, stream>>>(a, tmE, tmF);                                                        \
-    return cudaGetLastError();                                                                                     \
+template <typename Real, int NGAS, int AMODE>
+int launch_integrate(const ufair_desc* d, const KArgs<Real>& a, cudaStream_t stream);
+
+template <typename Real, int NGAS, int AMODE, int GPL, unsigned FORM>
+int launch_variant(const ufair_desc* d, const KArgs<Real>& a, cudaStream_t stream) {
+  using WS = WarpSmem<Real, NGAS, AMODE, GPL>;
+  CUtensorMap tmE, tmF;  // box = WS::MW members x kTT steps (x NGAS gases): depends on the lane mapping
+  const int rc = make_tensor_maps(d, sizeof(Real), WS::MW, &tmE, &tmF);
+  if (rc != UFAIR_OK) return rc;
+  const size_t smem = (size_t)WS::bytes(a.fext_mode == UFAIR_FEXT_MEMBER) * kWarps;
+  auto kern = (a.e_mode == UFAIR_E_MEMBER) ? ufair_integrate_kernel<Real, NGAS, AMODE, true, GPL, FORM>
+                                            : ufair_integrate_kernel<Real, NGAS, AMODE, false, GPL, FORM>;
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return cuda_error(e, "cudaFuncSetAttribute(ufair_integrate_kernel)");
+  const long long n_warp = (a.n_member + WS::MW - 1) / WS::MW;
+  const unsigned grid = (unsigned)((n_warp + kWarps - 1) / kWarps);
+  kern<<<grid, kWarps * 32, smem, stream>>>(a, tmE, tmF);
+  e = cudaGetLastError();
+  return e == cudaSuccess ? UFAIR_OK : cuda_error(e, "ufair_integrate_kernel launch");
+}
+
+// the descriptor's gas_form bytes, packed like the FORM template argument
+inline unsigned requested_form(const ufair_desc* d) {
+  unsigned f = 0;
+  for (int g = 0; g < d->n_gas; ++g) f |= (unsigned)d->gas_form[g] << (8 * g);
+  return f;
+}
+
+// the instantiated form the dispatcher uses for this descriptor (0 = the dense kernel)
+inline unsigned pick_form(const ufair_desc* d) {
+  const unsigned want = requested_form(d);
+  if (want == 0 || d->alpha_mode != UFAIR_ALPHA_EXP) return 0;
+  const unsigned* tab = d->n_gas == 1 ? kForms1 : d->n_gas == 2 ? kForms2 : d->n_gas == 3 ? kForms3 : kForms4;
+  const int n = d->n_gas == 1 ? (int)(sizeof(kForms1) / sizeof(unsigned)) : 1;
+  for (int k = 0; k < n; ++k)
+    if (form_covers(tab[k], want, d->n_gas)) return tab[k];
+  return 0;
+}
+
+// dense launcher, and the specialised forms of the EXP alpha mode when the descriptor's gas_form allows
+#define UFAIR_TRY_FORM(Real, NGAS, F) \
+  if (form == F) return launch_variant<Real, NGAS, UFAIR_ALPHA_EXP, NGAS, F>(d, a, stream);
+
+#define UFAIR_DEFINE_LAUNCH_EXP(Real, NGAS, TRY_FORMS)                                                 \
+  template <> int launch_integrate<Real, NGAS, UFAIR_ALPHA_EXP>(const ufair_desc* d, const KArgs<Real>& a, \
+                                                                cudaStream_t stream) {                 \
+    const unsigned form = pick_form(d);                                                                \
+    TRY_FORMS                                                                                          \
+    return launch_variant<Real, NGAS, UFAIR_ALPHA_EXP, gases_per_lane(sizeof(Real), NGAS), 0u>(d, a, stream); \
+  }
+
+#define UFAIR_DEFINE_LAUNCH(Real, NGAS, AMODE)                                                         \
+  template <> int launch_integrate<Real, NGAS, AMODE>(const ufair_desc* d, const KArgs<Real>& a,       \
+                                                      cudaStream_t stream) {                           \
+    return launch_variant<Real, NGAS, AMODE, gases_per_lane(sizeof(Real), NGAS), 0u>(d, a, stream);    \
   }
 
 }  // namespace ufair

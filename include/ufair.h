@@ -40,7 +40,7 @@
 extern "C" {
 #endif
 
-#define UFAIR_ABI_VERSION 1
+#define UFAIR_ABI_VERSION 2
 
 #define UFAIR_MAX_GAS 4
 #define UFAIR_N_POOL 4
@@ -82,6 +82,16 @@ enum { UFAIR_ALPHA_EXP = 0,    /* alpha = g0 * exp(iIRF/g1)      (the "derived f
 enum { UFAIR_T_MID = 0,  /* T = sum_j (S_j + S_j')/2 */
        UFAIR_T_END = 1   /* T = sum_j S_j'           */ };
 enum { UFAIR_OUT_C = 1, UFAIR_OUT_RF = 2, UFAIR_OUT_T = 4, UFAIR_OUT_ALPHA = 8 };
+
+/* gas_form[g]: what gas g actually uses, so that the library may pick a kernel that skips the rest.
+ * 0 = unspecified (four pools, all three forcing terms).  Otherwise UFAIR_FORM(n_pool, terms):
+ * only pools 1..n_pool carry mass (a_i == 0 and zero initial state for the others) and only the
+ * forcing terms in `terms` have non-zero coefficients -- for EVERY member of the call.  It is a
+ * promise by the caller (ufair_detect_form_* derives it from the parameter arrays); results are
+ * those of the unspecialised kernel.  One-pool gases are the reference's own case
+ * (U_FaIR/concentrations.py:4-5 is a single box). */
+enum { UFAIR_TERM_LOG = 1, UFAIR_TERM_LIN = 2, UFAIR_TERM_SQRT = 4 };
+#define UFAIR_FORM(n_pool, terms) ((uint8_t)((n_pool) | ((terms) << 4)))
 
 /* moments_private / moments rows */
 enum { UFAIR_MOM_SUM = 0, UFAIR_MOM_SUMSQ = 1, UFAIR_MOM_MIN = 2, UFAIR_MOM_MAX = 3, UFAIR_MOM_COUNT = 4 };
@@ -152,6 +162,10 @@ typedef struct ufair_desc {
   uint32_t* hist_private;   /* [hist_copies][hist_rows][hist_bins] */
   double* moments_private;  /* [hist_copies][hist_rows][UFAIR_MOM_COUNT]: member slice c of every
                                row is folded into copy c, in a fixed order (deterministic) */
+
+  /* ---- optional per-gas specialisation (see UFAIR_FORM) ---- */
+  uint8_t gas_form[UFAIR_MAX_GAS];
+  uint32_t reserved1;
 } ufair_desc;
 
 /* ---- version / errors ---- */
@@ -165,6 +179,18 @@ int64_t ufair_block_members(void);
 /* ---- the hot path: oxfair (driver loop) with step_conc/alpha_val/step_forc/step_temp fused ---- */
 int ufair_run_f64(const ufair_desc* d, void* stream);
 int ufair_run_f32(const ufair_desc* d, void* stream);
+
+/* Derive gas_form from the descriptor's DEVICE parameter arrays (gas_params, state_in): scans every
+ * member, writes n_gas bytes to the HOST array `form` and synchronises `stream`.
+ * `scratch` is a device buffer of at least UFAIR_MAX_GAS int32. */
+int ufair_detect_form_f64(const ufair_desc* d, int32_t* scratch, uint8_t* form, void* stream);
+int ufair_detect_form_f32(const ufair_desc* d, int32_t* scratch, uint8_t* form, void* stream);
+
+/* Which integrator variant ufair_run_* launches for this descriptor (informational / tests):
+ * *form = the specialised per-gas form in use, packed one UFAIR_FORM byte per gas (0 = the general
+ * kernel), *gases_per_lane and *members_per_warp = the lane mapping.  elem_size: 8 (f64) or 4 (f32). */
+int ufair_kernel_variant(const ufair_desc* d, int32_t elem_size, uint32_t* form, int32_t* gases_per_lane,
+                         int32_t* members_per_warp);
 
 /* Zero (and initialise the min/max sentinels of) the private statistics buffers. */
 int ufair_stats_reset(const ufair_desc* d, void* stream);

@@ -72,6 +72,8 @@ def oxfair(emissions, gas_params, thermal_params, *, dt=1.0, scen_idx=None, e_sc
     fx = _f64(f_ext)
     if fx is not None and fx.ndim == 1:
         fx = fx[:, None].copy()
+    if fx is not None and shared and not fext_per_member and fx.shape[1] == 1 and E.shape[2] > 1:
+        fx = np.ascontiguousarray(np.broadcast_to(fx, (n_t, E.shape[2])))   # one shared series for every scenario
     st_in = _f64(state_in)
     want = set(outputs) | ({"alpha"} if want_alpha else set())
     out = {}

@@ -153,3 +153,18 @@ def test_bench_reference_arm_contract():
     assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1
     assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["value"] == d["value"]
     assert "workload" in d["config"]
+
+
+def test_gas_form_spelling_and_flop_convention():
+    from fiveeqscm_b200 import _abi
+    from fiveeqscm_b200.concentrations import _form_byte
+    import bench
+    assert _form_byte(None) == 0 and _form_byte(0) == 0
+    assert _form_byte((1, "lin+sqrt")) == _abi.form(1, _abi.TERM_LIN | _abi.TERM_SQRT) == 0x61
+    assert _form_byte((4, ("log",))) == 0x14 and _form_byte(0x21) == 0x21
+    for bad in ((0, "lin"), (5, "lin"), (1, "cube"), 0x85, 0x06):
+        with pytest.raises(ValueError):
+            _form_byte(bad)
+    # the survey's 751 flops per member-step is the four-pool, three-term case of the per-form count
+    assert bench.algorithmic_flops((0, 0, 0)) == bench.FLOPS_PER_STEP == 751.0
+    assert bench.algorithmic_flops((0x14, 0x41, 0x41)) == 236 + 2 * 102 + 13
