@@ -28,7 +28,7 @@ E_MEMBER, E_SCENARIO = 0, 1
 FEXT_NONE, FEXT_SCENARIO, FEXT_MEMBER = 0, 1, 2
 ALPHA_EXP, ALPHA_SINH, ALPHA_NEWTON, ALPHA_ONE = 0, 1, 2, 3
 T_MID, T_END = 0, 1
-OUT_C, OUT_RF, OUT_T, OUT_ALPHA = 1, 2, 4, 8
+OUT_C, OUT_RF, OUT_T, OUT_ALPHA, OUT_E = 1, 2, 4, 8, 16
 MOM_SUM, MOM_SUMSQ, MOM_MIN, MOM_MAX, MOM_COUNT = 0, 1, 2, 3, 4
 
 OK, ERR_ARG, ERR_ALIGN, ERR_CUDA, ERR_UNSUPPORTED, ERR_NOMEM = 0, -1, -2, -3, -4, -5
@@ -79,7 +79,8 @@ class UfairDesc(C.Structure):
         ("hist_private", C.c_void_p),
         ("moments_private", C.c_void_p),
         ("gas_form", C.c_uint8 * 4),
-        ("reserved1", C.c_uint32),
+        ("conc_driven", C.c_int32),
+        ("out_E", C.c_void_p),
     ]
 
     def __init__(self, **kw):

@@ -26,7 +26,7 @@ from . import _abi
 
 _ALPHA = {"exp": _abi.ALPHA_EXP, "sinh": _abi.ALPHA_SINH, "newton": _abi.ALPHA_NEWTON, "one": _abi.ALPHA_ONE}
 _TMODE = {"mid": _abi.T_MID, "end": _abi.T_END}
-_OUT = {"C": _abi.OUT_C, "RF": _abi.OUT_RF, "T": _abi.OUT_T, "alpha": _abi.OUT_ALPHA}
+_OUT = {"C": _abi.OUT_C, "RF": _abi.OUT_RF, "T": _abi.OUT_T, "alpha": _abi.OUT_ALPHA, "E": _abi.OUT_E}
 
 
 def _torch():
@@ -56,6 +56,7 @@ class EnsembleResult:
     RF: object = None       # [n_gas][n_t][n_member]
     T: object = None        # [n_t][n_member]
     alpha: object = None    # [n_gas][n_t][n_member] (diagnostic)
+    E: object = None        # [n_gas][n_t][n_member] emission rates (diagnosed for concentration-driven gases)
     state: object = None    # [5 n_gas + 3][n_member]  -> pass as state_in to continue the run
     hist: object = None     # [n_t][bins] int64 counts (this rank's members)
     moments: object = None  # [n_t][4] float64: sum, sumsq, min, max of T over members
@@ -124,7 +125,7 @@ def _round_up(n, m):
 
 
 def _build_desc(G, n_t, M, ld, n_scen, e_scen, fext_mode, alpha_mode, newton_iters, t_mode, outputs, dt, iirf_h,
-                iirf_max, stats: Optional[HistSpec], gas_form=None):
+                iirf_max, stats: Optional[HistSpec], gas_form=None, conc_driven=None):
     if alpha_mode not in _ALPHA:
         raise ValueError(f"alpha_mode must be one of {sorted(_ALPHA)}")
     if t_mode not in _TMODE:
@@ -143,12 +144,35 @@ def _build_desc(G, n_t, M, ld, n_scen, e_scen, fext_mode, alpha_mode, newton_ite
         d.hist_bins, d.hist_copies = int(stats.bins), int(stats.copies)
         d.hist_lo, d.hist_hi = float(stats.lo), float(stats.hi)
         d.hist_t0, d.hist_rows = 0, n_t
+    d.conc_driven = _driven_mask(conc_driven, G)
     if gas_form is not None and not isinstance(gas_form, str):
         if len(gas_form) != G:
             raise ValueError("gas_form must have one entry per gas")
         for g, f in enumerate(gas_form):
             d.gas_form[g] = _form_byte(f)
     return d
+
+
+def _driven_mask(conc_driven, G) -> int:
+    """None / False -> 0; True -> every gas; else one truth value per gas."""
+    if conc_driven is None or conc_driven is False:
+        return 0
+    if conc_driven is True:
+        return (1 << G) - 1
+    flags = list(conc_driven)
+    if len(flags) != G:
+        raise ValueError("conc_driven must be a bool or one flag per gas")
+    return sum(1 << g for g, f in enumerate(flags) if f)
+
+
+def _with_E(outputs, conc_driven):
+    """Concentration-driven runs always return the diagnosed emissions."""
+    outputs = tuple(outputs)
+    if conc_driven is None or isinstance(conc_driven, bool):
+        driven = bool(conc_driven)
+    else:
+        driven = any(bool(f) for f in conc_driven)
+    return outputs + ("E",) if driven and "E" not in outputs else outputs
 
 
 def _form_byte(f) -> int:
@@ -175,7 +199,7 @@ def run_ensemble(emissions, gas_params, thermal_params, *, dt=1.0, scen_idx=None
                  fext_per_member=False, state_in=None, alpha_mode="exp", newton_iters=0, iirf_max=None,
                  iirf_h=100.0, t_mode="mid", outputs: Sequence[str] = ("C", "RF", "T"), stats: Optional[HistSpec] = None,
                  precision="f64", return_state=True, chunk_members=65536, workspace=None, out=None,
-                 gas_form="auto") -> EnsembleResult:
+                 gas_form="auto", conc_driven=None) -> EnsembleResult:
     """Integrate the 5-equation model for an ensemble (oxfair, .coveragerc:19, as one kernel launch).
 
     emissions      [G][n_t][M] per-member emission RATES, or [G][n_t][S] scenario-shared with
@@ -188,6 +212,9 @@ def run_ensemble(emissions, gas_params, thermal_params, *, dt=1.0, scen_idx=None
     alpha_mode     "exp" | "sinh" | "newton" (``newton_iters`` fixed steps) | "one".
     outputs        any of "C", "RF", "T", "alpha".   stats: HistSpec -> per-step T histogram + moments.
     precision      "f64" (default; <= 1e-10 relative vs the float64 oracle) or "f32" (<= 1e-4 K in T).
+    conc_driven    None, True (every gas) or one flag per gas: those gases' ``emissions`` rows are the
+                   CONCENTRATION to reach at the end of each step; the emission rate that does so
+                   is diagnosed (step_conc inverted exactly) and returned as ``.E`` (all gases).
     gas_form       per-gas specialisation (include/ufair.h UFAIR_FORM): "auto" scans the parameters on
                    the device and lets the library skip pools with a_i == 0 and forcing terms whose
                    coefficient is zero for every member (CUDA inputs; the host pipeline treats
@@ -206,10 +233,10 @@ def run_ensemble(emissions, gas_params, thermal_params, *, dt=1.0, scen_idx=None
     if on_device:
         return _run_device(torch, emissions, gas_params, thermal_params, dt, scen_idx, e_scale, f_ext,
                            fext_per_member, state_in, alpha_mode, newton_iters, iirf_max, iirf_h, t_mode,
-                           tuple(outputs), stats, precision, return_state, gas_form)
+                           _with_E(outputs, conc_driven), stats, precision, return_state, gas_form, conc_driven)
     return _run_host(torch, emissions, gas_params, thermal_params, dt, scen_idx, e_scale, f_ext, fext_per_member,
-                     state_in, alpha_mode, newton_iters, iirf_max, iirf_h, t_mode, tuple(outputs), stats, precision,
-                     return_state, chunk_members, workspace, out, gas_form)
+                     state_in, alpha_mode, newton_iters, iirf_max, iirf_h, t_mode, _with_E(outputs, conc_driven), stats,
+                     precision, return_state, chunk_members, workspace, out, gas_form, conc_driven)
 
 
 def _shapes(E_shape, gp_shape, tp_shape, scen_idx, fext_shape, fext_per_member):
@@ -249,8 +276,10 @@ class DevicePlan:
 
     def __init__(self, E, gp, tp, *, dt=1.0, scen_idx=None, e_scale=None, f_ext=None, fext_per_member=False,
                  state_in=None, alpha_mode="exp", newton_iters=0, iirf_max=None, iirf_h=100.0, t_mode="mid",
-                 outputs=("C", "RF", "T"), stats=None, precision="f64", return_state=True, gas_form="auto"):
+                 outputs=("C", "RF", "T"), stats=None, precision="f64", return_state=True, gas_form="auto",
+                 conc_driven=None):
         torch = _require_cuda()
+        outputs = _with_E(outputs, conc_driven)
         self._L = _abi.lib()
         dtype = torch.float64 if precision == "f64" else torch.float32
         es = 8 if precision == "f64" else 4
@@ -283,7 +312,7 @@ class DevicePlan:
         gp_d, tp_d = member_rows(gp, "gas_params"), member_rows(tp, "thermal_params")
         keep += [E_d, gp_d, tp_d]
         d = _build_desc(G, n_t, M, ld, n_scen, e_scen, fext_mode, alpha_mode, newton_iters, t_mode, outputs, dt,
-                        iirf_h, iirf_max, stats, gas_form)
+                        iirf_h, iirf_max, stats, gas_form, conc_driven)
         d.emissions, d.gas_params, d.thermal_params = E_d.data_ptr(), gp_d.data_ptr(), tp_d.data_ptr()
         if scen_idx is not None:
             si = torch.as_tensor(scen_idx, device=dev).to(torch.int32).contiguous()
@@ -324,6 +353,8 @@ class DevicePlan:
             self._t_scratch = new(n_t, ld); d.out_T = self._t_scratch.data_ptr()
         if "alpha" in outputs:
             buf = new(G, n_t, ld); d.out_alpha = buf.data_ptr(); res.alpha = buf[..., :M]
+        if "E" in outputs:
+            buf = new(G, n_t, ld); d.out_E = buf.data_ptr(); res.E = buf[..., :M]
         if return_state:
             buf = new(_abi.state_rows(G), ld); d.state_out = buf.data_ptr(); res.state = buf[..., :M]
         if stats is not None:
@@ -388,11 +419,12 @@ class DevicePlan:
 
 
 def _run_device(torch, E, gp, tp, dt, scen_idx, e_scale, f_ext, fext_per_member, state_in, alpha_mode, newton_iters,
-                iirf_max, iirf_h, t_mode, outputs, stats, precision, return_state, gas_form="auto"):
+                iirf_max, iirf_h, t_mode, outputs, stats, precision, return_state, gas_form="auto", conc_driven=None):
     return DevicePlan(E, gp, tp, dt=dt, scen_idx=scen_idx, e_scale=e_scale, f_ext=f_ext,
                       fext_per_member=fext_per_member, state_in=state_in, alpha_mode=alpha_mode,
                       newton_iters=newton_iters, iirf_max=iirf_max, iirf_h=iirf_h, t_mode=t_mode, outputs=outputs,
-                      stats=stats, precision=precision, return_state=return_state, gas_form=gas_form).run()
+                      stats=stats, precision=precision, return_state=return_state, gas_form=gas_form,
+                      conc_driven=conc_driven).run()
 
 
 class Workspace:
@@ -416,7 +448,7 @@ class Workspace:
 
 def _run_host(torch, E, gp, tp, dt, scen_idx, e_scale, f_ext, fext_per_member, state_in, alpha_mode, newton_iters,
               iirf_max, iirf_h, t_mode, outputs, stats, precision, return_state, chunk_members, workspace, out=None,
-              gas_form=None):
+              gas_form=None, conc_driven=None):
     L = _abi.lib()
     npdt = np.float64 if precision == "f64" else np.float32
 
@@ -431,7 +463,7 @@ def _run_host(torch, E, gp, tp, dt, scen_idx, e_scale, f_ext, fext_per_member, s
     fshape = None if f_ext is None else f_ext.shape
     G, n_t, M, e_scen, n_scen, fext_mode = _shapes(E.shape, gp.shape, tp.shape, scen_idx, fshape, fext_per_member)
     d = _build_desc(G, n_t, M, M, n_scen, e_scen, fext_mode, alpha_mode, newton_iters, t_mode, outputs, dt, iirf_h,
-                    iirf_max, stats, gas_form)
+                    iirf_max, stats, gas_form, conc_driven)
     d.emissions, d.gas_params, d.thermal_params = E.ctypes.data, gp.ctypes.data, tp.ctypes.data
     keep = [E, gp, tp]
     if scen_idx is not None:
@@ -473,6 +505,8 @@ def _run_host(torch, E, gp, tp, dt, scen_idx, e_scale, f_ext, fext_per_member, s
         d.out_T = host_out("T", (n_t, M), npdt)
     if "alpha" in outputs:
         d.out_alpha = host_out("alpha", (G, n_t, M), npdt)
+    if "E" in outputs:
+        d.out_E = host_out("E", (G, n_t, M), npdt)
     if return_state:
         d.state_out = host_out("state", (_abi.state_rows(G), M), npdt)
     hist_p = mom_p = None
@@ -505,6 +539,8 @@ def pinned_result(n_gas, n_t, n_member, outputs=("C", "RF", "T"), stats: Optiona
         r.T = pin(n_t, n_member)
     if "alpha" in outputs:
         r.alpha = pin(n_gas, n_t, n_member)
+    if "E" in outputs:
+        r.E = pin(n_gas, n_t, n_member)
     if return_state:
         r.state = pin(_abi.state_rows(n_gas), n_member)
     if stats is not None:

@@ -57,6 +57,9 @@ int validate_desc(const ufair_desc* d, size_t elem) {
   if ((d->out_mask & UFAIR_OUT_RF) && !d->out_RF) return set_error(UFAIR_ERR_ARG, "out_RF requested but NULL");
   if ((d->out_mask & UFAIR_OUT_T) && !d->out_T) return set_error(UFAIR_ERR_ARG, "out_T requested but NULL");
   if ((d->out_mask & UFAIR_OUT_ALPHA) && !d->out_alpha) return set_error(UFAIR_ERR_ARG, "out_alpha requested but NULL");
+  if ((d->out_mask & UFAIR_OUT_E) && !d->out_E) return set_error(UFAIR_ERR_ARG, "out_E requested but NULL");
+  if (d->conc_driven < 0 || d->conc_driven >= (1 << d->n_gas))
+    return set_error(UFAIR_ERR_ARG, "conc_driven 0x%x names a gas >= n_gas %d", d->conc_driven, d->n_gas);
   // TMA bulk-copy sources
   if (d->e_mode == UFAIR_E_MEMBER && misaligned(d->emissions))
     return set_error(UFAIR_ERR_ALIGN, "emissions must be 16-byte aligned");
@@ -100,6 +103,8 @@ template <typename Real> static KArgs<Real> make_args(const ufair_desc* d) {
   a.oRF = (Real*)d->out_RF;
   a.oT = (Real*)d->out_T;
   a.oA = (Real*)d->out_alpha;
+  a.oE = (Real*)d->out_E;
+  a.conc_driven = d->conc_driven;
   a.state_out = (Real*)d->state_out;
   a.hist_bins = d->hist_bins;
   a.hist_copies = d->hist_copies;

@@ -36,7 +36,7 @@ struct DevBuf {
   }
 };
 
-enum { B_E, B_FEXT, B_GP, B_TP, B_SIN, B_SCEN, B_ESC, B_OC, B_ORF, B_OT, B_OA, B_SOUT, B_COUNT };
+enum { B_E, B_FEXT, B_GP, B_TP, B_SIN, B_SCEN, B_ESC, B_OC, B_ORF, B_OT, B_OA, B_OE, B_SOUT, B_COUNT };
 
 struct Stage {
   DevBuf b[B_COUNT];
@@ -98,6 +98,7 @@ static int run_chunks(ufair_workspace* ws, const ufair_desc* h, const ufair_desc
                          {B_ORF, (size_t)G * n_t, (h->out_mask & UFAIR_OUT_RF) != 0},
                          {B_OT, (size_t)n_t, (h->out_mask & UFAIR_OUT_T) != 0 || h->stats != 0},  // moments pass reads T
                          {B_OA, (size_t)G * n_t, (h->out_mask & UFAIR_OUT_ALPHA) != 0},
+                         {B_OE, (size_t)G * n_t, (h->out_mask & UFAIR_OUT_E) != 0},
                          {B_SOUT, srows, h->state_out != nullptr}};
     if (S.used) {  // staging of chunk c-2: inputs consumed by its kernel, outputs copied out
       CK(cudaStreamWaitEvent(ws->s_in, S.run_done, 0), "cudaStreamWaitEvent");
@@ -148,6 +149,7 @@ static int run_chunks(ufair_workspace* ws, const ufair_desc* h, const ufair_desc
     k.out_RF = S.b[B_ORF].p;
     k.out_T = S.b[B_OT].p;
     k.out_alpha = S.b[B_OA].p;
+    k.out_E = S.b[B_OE].p;
     k.state_out = h->state_out ? S.b[B_SOUT].p : nullptr;
     rc = run_device<Real>(&k, ws->s_run);
     if (rc == UFAIR_OK && h->stats) rc = run_moments<Real>(&k, ws->s_run);
@@ -163,6 +165,8 @@ static int run_chunks(ufair_workspace* ws, const ufair_desc* h, const ufair_desc
       rc = copy2d(hdst(h->out_T), hp, S.b[B_OT].p, dp, w, n_t, cudaMemcpyDeviceToHost, ws->s_out);
     if (rc == UFAIR_OK && (h->out_mask & UFAIR_OUT_ALPHA))
       rc = copy2d(hdst(h->out_alpha), hp, S.b[B_OA].p, dp, w, (size_t)G * n_t, cudaMemcpyDeviceToHost, ws->s_out);
+    if (rc == UFAIR_OK && (h->out_mask & UFAIR_OUT_E))
+      rc = copy2d(hdst(h->out_E), hp, S.b[B_OE].p, dp, w, (size_t)G * n_t, cudaMemcpyDeviceToHost, ws->s_out);
     if (rc == UFAIR_OK && h->state_out)
       rc = copy2d(hdst(h->state_out), hp, S.b[B_SOUT].p, dp, w, srows, cudaMemcpyDeviceToHost, ws->s_out);
     if (rc != UFAIR_OK) return rc;

@@ -146,6 +146,8 @@ template <typename Real> struct KArgs {
   Real* oRF;
   Real* oT;
   Real* oA;
+  Real* oE;
+  int conc_driven;  // bit g: gas g's input rows are target concentrations (INV kernels only)
   Real* state_out;
   int hist_bins, hist_copies, hist_t0, hist_rows;
   Real hist_lo, hist_invw;
@@ -267,8 +269,9 @@ template <typename Real> __device__ __forceinline__ Real sum_pools(const Real (&
   return R[0];
 }
 
-// GPL: gases per lane (1 or NGAS); FORM: per-gas specialisation (0 = dense; needs GPL == NGAS)
-template <typename Real, int NGAS, int AMODE, bool EMEM, int GPL_, unsigned FORM>
+// GPL: gases per lane (1 or NGAS); FORM: per-gas specialisation (0 = dense; needs GPL == NGAS);
+// INV: concentration-driven gases (diagnose the emissions) and the emissions output
+template <typename Real, int NGAS, int AMODE, bool EMEM, int GPL_, unsigned FORM, bool INV>
 __global__ void __launch_bounds__(kWarps * 32, min_blocks(sizeof(Real), NGAS, GPL_, FORM))
     ufair_integrate_kernel(const __grid_constant__ KArgs<Real> a, const __grid_constant__ CUtensorMap tmE,
                            const __grid_constant__ CUtensorMap tmF) {
@@ -436,15 +439,17 @@ __global__ void __launch_bounds__(kWarps * 32, min_blocks(sizeof(Real), NGAS, GP
 
   // output predicates packed in one register; running output pointers (gas g0; + gl * gstride)
   const bool owner = active && (g0 == 0);  // the lane that owns the member's T / histogram count
-  unsigned wm = (active ? (unsigned)(a.out_mask & (UFAIR_OUT_C | UFAIR_OUT_RF | UFAIR_OUT_ALPHA)) : 0u) |
+  constexpr unsigned WM_STATS = 0x100u;
+  unsigned wm = (active ? (unsigned)(a.out_mask & (UFAIR_OUT_C | UFAIR_OUT_RF | UFAIR_OUT_ALPHA | (INV ? UFAIR_OUT_E : 0))) : 0u) |
                 ((owner && ((a.out_mask & UFAIR_OUT_T) || a.stats)) ? (unsigned)UFAIR_OUT_T : 0u) |
-                ((owner && a.stats) ? 16u : 0u);
+                ((owner && a.stats) ? WM_STATS : 0u);
   pin(wm);
   const long long gstride = (long long)n_t * ld;
   const long long o_gas = (long long)g0 * gstride + m_raw;
   Real* pC = a.oC + o_gas;
   Real* pRF = a.oRF + o_gas;
   const long long dA = a.oA - a.oC;  // the (diagnostic) alpha output is addressed relative to pC
+  const long long dE = INV ? (a.oE - a.oC) : 0;  // and so is the emissions output
   Real* pT = a.oT + m_raw;
   unsigned int* hrow = a.stats ? a.hist + ((size_t)(wg % a.hist_copies) * a.hist_rows + a.hist_t0) * a.hist_bins : nullptr;
   const int bins_m1 = a.hist_bins - 1;
@@ -520,11 +525,25 @@ __global__ void __launch_bounds__(kWarps * 32, min_blocks(sizeof(Real), NGAS, GP
         inva = M::rcp(alpha);
       }
       // ---- step_conc: relax each pool toward its equilibrium  E alpha c a_i tau_i
-      const Real ea = e * alpha;
       Real mq[4];
 #pragma unroll
       for (int q = 0; q < 4; ++q)
         if (q < NP) mq[q] = (AMODE == UFAIR_ALPHA_ONE) ? PARG(gl, G_K0 + q) : M::decay(PARG(gl, G_K0 + q) * inva);
+      if (INV) {
+        // concentration-driven gas: `e` is the target C; step_conc is linear in E, so
+        //   E = (C_target - C0 - sum R_i (1 - m_i)) / (alpha sum m_i c a_i tau_i)
+        Real keep = 0, gain = 0;
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+          if (q < NP) {
+            keep += fma(-mq[q], R[gl][q], R[gl][q]);
+            gain = fma(mq[q], PARG(gl, G_KA0 + q), gain);
+          }
+        const Real e_inv = ((e - PARG(gl, G_C0)) - keep) * M::rcp(gain * alpha);
+        if ((a.conc_driven >> (g0 + gl)) & 1) e = e_inv;
+        if (wm & UFAIR_OUT_E) st_stream(pC + dE + gl * gstride, e);
+      }
+      const Real ea = e * alpha;
 #pragma unroll
       for (int q = 0; q < 4; ++q)
         if (q < NP) R[gl][q] = fma(mq[q], fma(ea, PARG(gl, G_KA0 + q), -R[gl][q]), R[gl][q]);
@@ -565,7 +584,7 @@ __global__ void __launch_bounds__(kWarps * 32, min_blocks(sizeof(Real), NGAS, GP
     Tprev = T;
     if (wm & UFAIR_OUT_T) st_stream(pT, T);
     pT += ld;
-    if (wm & 16u) {  // owner lane of a real member: one histogram count
+    if (wm & WM_STATS) {  // owner lane of a real member: one histogram count
       const Real x = M::bin_x(T, a.hist_lo, a.hist_invw);
       if (x == x) {
         const int b = max(0, min(bins_m1, M::floor_to_int(x)));
@@ -679,15 +698,15 @@ int cuda_error(cudaError_t e, const char* what);
 template <typename Real, int NGAS, int AMODE>
 int launch_integrate(const ufair_desc* d, const KArgs<Real>& a, cudaStream_t stream);
 
-template <typename Real, int NGAS, int AMODE, int GPL, unsigned FORM>
+template <typename Real, int NGAS, int AMODE, int GPL, unsigned FORM, bool INV = false>
 int launch_variant(const ufair_desc* d, const KArgs<Real>& a, cudaStream_t stream) {
   using WS = WarpSmem<Real, NGAS, AMODE, GPL>;
   CUtensorMap tmE, tmF;  // box = WS::MW members x kTT steps (x NGAS gases): depends on the lane mapping
   const int rc = make_tensor_maps(d, sizeof(Real), WS::MW, &tmE, &tmF);
   if (rc != UFAIR_OK) return rc;
   const size_t smem = (size_t)WS::bytes(a.fext_mode == UFAIR_FEXT_MEMBER) * kWarps;
-  auto kern = (a.e_mode == UFAIR_E_MEMBER) ? ufair_integrate_kernel<Real, NGAS, AMODE, true, GPL, FORM>
-                                            : ufair_integrate_kernel<Real, NGAS, AMODE, false, GPL, FORM>;
+  auto kern = (a.e_mode == UFAIR_E_MEMBER) ? ufair_integrate_kernel<Real, NGAS, AMODE, true, GPL, FORM, INV>
+                                            : ufair_integrate_kernel<Real, NGAS, AMODE, false, GPL, FORM, INV>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return cuda_error(e, "cudaFuncSetAttribute(ufair_integrate_kernel)");
   const long long n_warp = (a.n_member + WS::MW - 1) / WS::MW;
@@ -705,9 +724,12 @@ inline unsigned requested_form(const ufair_desc* d) {
 }
 
 // the instantiated form the dispatcher uses for this descriptor (0 = the dense kernel)
+// concentration-driven gases / the emissions output run on the INV instantiation of the general kernel
+inline bool wants_inverse(const ufair_desc* d) { return d->conc_driven != 0 || (d->out_mask & UFAIR_OUT_E) != 0; }
+
 inline unsigned pick_form(const ufair_desc* d) {
   const unsigned want = requested_form(d);
-  if (want == 0 || d->alpha_mode != UFAIR_ALPHA_EXP) return 0;
+  if (want == 0 || d->alpha_mode != UFAIR_ALPHA_EXP || wants_inverse(d)) return 0;
   const unsigned* tab = d->n_gas == 1 ? kForms1 : d->n_gas == 2 ? kForms2 : d->n_gas == 3 ? kForms3 : kForms4;
   const int n = d->n_gas == 1 ? (int)(sizeof(kForms1) / sizeof(unsigned)) : 1;
   for (int k = 0; k < n; ++k)
@@ -724,12 +746,16 @@ inline unsigned pick_form(const ufair_desc* d) {
                                                                 cudaStream_t stream) {                 \
     const unsigned form = pick_form(d);                                                                \
     TRY_FORMS                                                                                          \
+    if (wants_inverse(d))                                                                              \
+      return launch_variant<Real, NGAS, UFAIR_ALPHA_EXP, gases_per_lane(sizeof(Real), NGAS), 0u, true>(d, a, stream); \
     return launch_variant<Real, NGAS, UFAIR_ALPHA_EXP, gases_per_lane(sizeof(Real), NGAS), 0u>(d, a, stream); \
   }
 
 #define UFAIR_DEFINE_LAUNCH(Real, NGAS, AMODE)                                                         \
   template <> int launch_integrate<Real, NGAS, AMODE>(const ufair_desc* d, const KArgs<Real>& a,       \
                                                       cudaStream_t stream) {                           \
+    if (wants_inverse(d))                                                                              \
+      return launch_variant<Real, NGAS, AMODE, gases_per_lane(sizeof(Real), NGAS), 0u, true>(d, a, stream); \
     return launch_variant<Real, NGAS, AMODE, gases_per_lane(sizeof(Real), NGAS), 0u>(d, a, stream);    \
   }
 

@@ -81,7 +81,7 @@ enum { UFAIR_ALPHA_EXP = 0,    /* alpha = g0 * exp(iIRF/g1)      (the "derived f
        UFAIR_ALPHA_ONE = 3     /* alpha == 1: no state dependence (HFC-style fixed lifetime)     */ };
 enum { UFAIR_T_MID = 0,  /* T = sum_j (S_j + S_j')/2 */
        UFAIR_T_END = 1   /* T = sum_j S_j'           */ };
-enum { UFAIR_OUT_C = 1, UFAIR_OUT_RF = 2, UFAIR_OUT_T = 4, UFAIR_OUT_ALPHA = 8 };
+enum { UFAIR_OUT_C = 1, UFAIR_OUT_RF = 2, UFAIR_OUT_T = 4, UFAIR_OUT_ALPHA = 8, UFAIR_OUT_E = 16 };
 
 /* gas_form[g]: what gas g actually uses, so that the library may pick a kernel that skips the rest.
  * 0 = unspecified (four pools, all three forcing terms).  Otherwise UFAIR_FORM(n_pool, terms):
@@ -165,7 +165,15 @@ typedef struct ufair_desc {
 
   /* ---- optional per-gas specialisation (see UFAIR_FORM) ---- */
   uint8_t gas_form[UFAIR_MAX_GAS];
-  uint32_t reserved1;
+
+  /* ---- concentration-driven gases (the inverse of step_conc) ----
+   * bit g set: rows emissions[g][..] hold the CONCENTRATION gas g must have at the end of each step;
+   * the integrator diagnoses the emission rate that produces it -- step_conc is linear in E:
+   *   E = (C_target - C0 - sum_i R_i (1 - m_i)) / (c sum_i a_i alpha tau_i m_i)
+   * -- and carries on with it (pools, G_cum, forcing, temperature).  out_E (UFAIR_OUT_E) receives
+   * the emission rate of every gas: diagnosed where the bit is set, the input otherwise. */
+  int32_t conc_driven;
+  void* out_E; /* [n_gas][n_t][ld_member] */
 } ufair_desc;
 
 /* ---- version / errors ---- */

@@ -59,7 +59,7 @@ def _f64(a):
 def oxfair(emissions, gas_params, thermal_params, *, dt=1.0, scen_idx=None, e_scale=None, f_ext=None,
            fext_per_member=False, e_scenario=None, state_in=None, alpha_mode=0, newton_iters=0,
            iirf_max=None, iirf_h=100.0, t_mode=0, want_alpha=False, outputs=("C", "RF", "T"),
-           n_threads=0):
+           n_threads=0, conc_driven=0):
     """C-oracle twin of oracle.ufair_oracle.oxfair (same arguments, float64 only)."""
     E = _f64(emissions)
     gp = _f64(gas_params)
@@ -85,6 +85,8 @@ def oxfair(emissions, gas_params, thermal_params, *, dt=1.0, scen_idx=None, e_sc
         out["T"] = np.empty((n_t, M))
     if "alpha" in want:
         out["alpha"] = np.empty((G, n_t, M))
+    if conc_driven or "E" in want:
+        out["E"] = np.empty((G, n_t, M))
     out["state"] = np.empty((_abi.state_rows(G), M))
     d = _abi.UfairDesc(
         n_gas=G, n_t=n_t, n_member=M, ld_member=M,
@@ -93,7 +95,8 @@ def oxfair(emissions, gas_params, thermal_params, *, dt=1.0, scen_idx=None, e_sc
         fext_mode=(_abi.FEXT_NONE if fx is None else (_abi.FEXT_MEMBER if fext_per_member else _abi.FEXT_SCENARIO)),
         alpha_mode=alpha_mode, newton_iters=newton_iters, t_mode=t_mode,
         out_mask=(_abi.OUT_C * ("C" in want) | _abi.OUT_RF * ("RF" in want) | _abi.OUT_T * ("T" in want)
-                  | _abi.OUT_ALPHA * ("alpha" in want)),
+                  | _abi.OUT_ALPHA * ("alpha" in want) | _abi.OUT_E * ("E" in out)),
+        conc_driven=int(conc_driven), out_E=_p(out.get("E")),
         dt=dt, iirf_h=iirf_h, iirf_max=(0.0 if iirf_max is None else float(iirf_max)),
         emissions=_p(E), scen_idx=_p(si), e_scale=_p(es), f_ext=_p(fx), gas_params=_p(gp),
         thermal_params=_p(tp), state_in=_p(st_in),

@@ -124,6 +124,7 @@ static void run_member(const ufair_desc* d, int64_t m) {
   double* oF = (d->out_mask & UFAIR_OUT_RF) ? (double*)d->out_RF : NULL;
   double* oT = (d->out_mask & UFAIR_OUT_T) ? (double*)d->out_T : NULL;
   double* oA = (d->out_mask & UFAIR_OUT_ALPHA) ? (double*)d->out_alpha : NULL;
+  double* oE = (d->out_mask & UFAIR_OUT_E) ? (double*)d->out_E : NULL;
 
   for (int t = 0; t < n_t; ++t) {
     double Ftot = 0.0;
@@ -142,6 +143,18 @@ static void run_member(const ufair_desc* d, int64_t m) {
                     GP(g, UFAIR_GP_RA) * Ga;
       if (clamp && iirf > d->iirf_max) iirf = d->iirf_max;
       double alpha = alpha_val(iirf, g0[g], g1[g], a[g], tau[g], d->alpha_mode, d->newton_iters, h);
+      /* concentration-driven gas: the input row is the target C; step_conc is linear in E, so
+       * E = (C_target - C0 - sum R_i (1 - m_i)) / (c sum a_i alpha tau_i m_i) */
+      if ((d->conc_driven >> g) & 1) {
+        double keep = 0.0, gain = 0.0;
+        for (int i = 0; i < 4; ++i) {
+          double at = alpha * tau[g][i];
+          double mi = -expm1(-dt / at);
+          keep = keep + R[g][i] * (1.0 - mi);
+          gain = gain + c * a[g][i] * at * mi;
+        }
+        e = (e - C0 - keep) / gain;
+      }
       /* step_conc (.coveragerc:12) */
       double sumR = 0.0;
       for (int i = 0; i < 4; ++i) {
@@ -162,6 +175,7 @@ static void run_member(const ufair_desc* d, int64_t m) {
       if (oC) oC[o] = C;
       if (oF) oF[o] = F;
       if (oA) oA[o] = alpha;
+      if (oE) oE[o] = e;
       Ftot = Ftot + F;
     }
     if (d->fext_mode == UFAIR_FEXT_SCENARIO) Ftot = Ftot + fx[(int64_t)t * d->n_scen + s];
