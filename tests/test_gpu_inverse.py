@@ -108,3 +108,25 @@ def test_inverse_argument_errors(api):
         _dev(api, ens["E"], ens, conc_driven=[True, False])          # one flag per gas
     d = _abi.UfairDesc(n_gas=3, n_t=4, n_member=8, ld_member=8, conc_driven=8)
     assert _abi.lib().ufair_run_f64(d, None) == _abi.ERR_ARG          # names gas 3 of 3
+
+
+def test_full_shard_round_trip(api):
+    """BASELINE configs[3], one GPU's shard (1.25e6 members x 736 steps x 3 gases): the oracle cannot
+    run that in seconds, the round trip can -- emissions -> concentrations (forward kernel) ->
+    emissions (concentration-driven kernel) must return the input, and the temperatures must agree."""
+    import torch
+    M, n_t = 1_250_000, 736
+    ens = ensemble(5000, n_t=n_t, dense=True, seed=77)
+    reps = (M + 4999) // 5000
+    tile = lambda x: to_dev(x).repeat(*([1] * (x.ndim - 1)), reps)[..., :M].contiguous()
+    gp, tp, E = tile(ens["gas_params"]), tile(ens["thermal_params"]), tile(ens["E"])
+    g = torch.Generator(device="cuda").manual_seed(99)
+    E *= 1 + 0.05 * torch.rand(3, 1, M, generator=g, device="cuda", dtype=torch.float64)   # members differ
+    fwd = api.run_ensemble(E, gp, tp, outputs=("C", "T"), return_state=False)
+    inv = api.run_ensemble(fwd.C, gp, tp, conc_driven=True, outputs=("T",), return_state=False)
+    torch.cuda.synchronize()
+    for gas in range(3):
+        scale = float(E[gas].abs().max())
+        err = float((inv.E[gas] - E[gas]).abs().max()) / scale
+        assert err < TOL64, f"gas {gas}: emissions come back with relative error {err:.2e}"
+    assert float((inv.T - fwd.T).abs().max()) / float(fwd.T.abs().max()) < TOL64
