@@ -11,11 +11,12 @@ def ensemble(M, n_t=736, dt=1.0, seed=20261018, dense=True, gases=P.GASES):
     return ens
 
 
-def field_relerr(got, ref):
-    """max |got - ref| / max |ref|: error relative to the field's own scale (the 1e-10 criterion)."""
+def field_relerr(got, ref, floor=0.0):
+    """max |got - ref| / max |ref|: error relative to the field's own scale (the 1e-10 criterion).
+    `floor` bounds the scale from below for fields that can be arbitrarily small (see tests/fuzz.py)."""
     got = np.asarray(got, dtype=np.float64)
     ref = np.asarray(ref, dtype=np.float64)
-    scale = np.max(np.abs(ref))
+    scale = max(float(np.max(np.abs(ref))) if ref.size else 0.0, floor)
     return float(np.max(np.abs(got - ref)) / (scale if scale > 0 else 1.0))
 
 
