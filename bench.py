@@ -87,37 +87,17 @@ def workload_config(args, n_gpus):
 # synthetic inputs on the device (same recipe as fiveeqscm_b200.params, torch RNG)
 # ------------------------------------------------------------------------------------------------
 def device_ensemble(torch, M, n_t, rank, dense):
-    from fiveeqscm_b200 import _abi
+    """Synthetic inputs of one rank, generated on its GPU by the product's own sampler
+    (ufair_sample_f64: Philox stream keyed by the GLOBAL member index, so the N ranks together hold
+    the one ensemble a single GPU would generate): perturbed parameters, a scenario index and an
+    emission scale per member; the per-member emission rows are the scenario rows times the scale."""
     from fiveeqscm_b200 import params as P
     dev = torch.device("cuda", torch.cuda.current_device())
-    g = torch.Generator(device=dev).manual_seed(20261018 + 1000 * rank)
-    gp0, tp0 = _dense_table(P) if dense else P.default_params(1)   # unperturbed parameter table
-    gp =torch.from_numpy(gp0).to(dev).repeat(1, 1, M).contiguous()
-    tp = torch.from_numpy(tp0).to(dev).repeat(1, M).contiguous()
-    rn = lambda *s: torch.randn(*s, generator=g, device=dev, dtype=torch.float64)
-    ln = lambda *s: torch.exp(0.1 * rn(*s))
-    nm = lambda *s: 1.0 + 0.13 * rn(*s)
-    gp[:, _abi.GP_TAU0:_abi.GP_TAU0 + 4] *= ln(N_GAS, 4, M)
-    a = gp[:, _abi.GP_A0:_abi.GP_A0 + 4] * ln(N_GAS, 4, M)
-    gp[:, _abi.GP_A0:_abi.GP_A0 + 4] = a / a.sum(dim=1, keepdim=True)
-    gp[:, _abi.GP_R0] *= ln(N_GAS, M)
-    for row in (_abi.GP_RU, _abi.GP_RT, _abi.GP_RA):
-        gp[:, row] *= nm(N_GAS, M)
-    gp[:, _abi.GP_F1:_abi.GP_F3 + 1] *= ln(N_GAS, 3, M)
-    tp *= ln(4, M)
+    gp, tp, scale, idx = P.sample_on_device(M, 20261018, first_member=rank * M, n_scen=4, dense_pools=dense)
     scen = torch.from_numpy(P.scenario_emissions(n_t)).to(dev)                  # [3][n_t][4]
-    idx = torch.randint(0, scen.shape[2], (M,), generator=g, device=dev)
-    scale = 1.0 + 0.05 * rn(N_GAS, M)
-    E = scen[:, :, idx]                                                           # [3][n_t][M]
+    E = scen[:, :, idx.long()]                                                    # [3][n_t][M]
     E *= scale[:, None, :]
-    return E.contiguous(), gp, tp
-
-
-def _dense_table(P):
-    class _Z:
-        def standard_normal(self, shape):
-            return np.zeros(shape)
-    return P.sample_params(1, _Z(), dense_pools=True)
+    return E.contiguous(), gp.contiguous(), tp.contiguous()
 
 
 # ------------------------------------------------------------------------------------------------

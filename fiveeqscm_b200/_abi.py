@@ -94,6 +94,34 @@ class UfairDesc(C.Structure):
             setattr(self, k, v)
 
 
+DIST_FIXED, DIST_LOGNORMAL, DIST_NORMAL = 0, 1, 2
+
+
+class UfairSampler(C.Structure):
+    """Mirror of `struct ufair_sampler` (include/ufair.h)."""
+    _fields_ = [
+        ("struct_size", C.c_uint32),
+        ("n_gas", C.c_int32),
+        ("seed", C.c_uint64),
+        ("n_scen", C.c_int32),
+        ("reserved", C.c_int32),
+        ("e_scale_sigma", C.c_double),
+        ("gas_base", (C.c_double * GP_COUNT) * MAX_GAS),
+        ("gas_sigma", (C.c_double * GP_COUNT) * MAX_GAS),
+        ("thermal_base", C.c_double * TP_COUNT),
+        ("thermal_sigma", C.c_double * TP_COUNT),
+        ("gas_dist", (C.c_uint8 * 24) * MAX_GAS),
+        ("thermal_dist", C.c_uint8 * 8),
+    ]
+
+    def __init__(self, **kw):
+        super().__init__()
+        self.struct_size = C.sizeof(UfairSampler)
+        self.n_scen = 1
+        for k, v in kw.items():
+            setattr(self, k, v)
+
+
 class UfairError(RuntimeError):
     def __init__(self, code: int, msg: str):
         super().__init__(f"libufair error {code}: {msg}")
@@ -125,6 +153,8 @@ SIGNATURES = {
     "ufair_g1g0_f64": (C.c_int, [_vp, _vp, _i64, _i64, _dbl, _i32, _vp, _vp, _vp]),
     "ufair_kq_f64": (C.c_int, [_vp, _vp, _vp, _vp, _dbl, _i64, _vp, _vp, _vp]),
     "ufair_hfc_pulse_f64": (C.c_int, [_vp, _vp, _vp, _i64, _vp]),
+    "ufair_sample_f64": (C.c_int, [C.POINTER(UfairSampler), _i64, _i64, _i64, _vp, _vp, _vp, _vp, _vp]),
+    "ufair_sample_f32": (C.c_int, [C.POINTER(UfairSampler), _i64, _i64, _i64, _vp, _vp, _vp, _vp, _vp]),
     "ufair_workspace_create": (C.c_int, [C.c_int, _i64, C.POINTER(_vp)]),
     "ufair_workspace_destroy": (C.c_int, [_vp]),
     "ufair_run_host_f64": (C.c_int, [_vp, C.POINTER(UfairDesc), _vp, _vp]),

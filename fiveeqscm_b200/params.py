@@ -146,3 +146,71 @@ def sample_ensemble(n_member: int, n_t: int = 736, dt: float = 1.0, seed: int = 
     f_ext = 0.1 * np.sin(2.0 * np.pi * (yr - 1765.0) / 11.0) - 0.2 * np.exp(-((yr - 1991.0) / 1.5) ** 2)
     return dict(gas_params=gp, thermal_params=tp, scen=scen, scen_idx=scen_idx, e_scale=e_scale,
                 f_ext=np.ascontiguousarray(f_ext))
+
+
+# ------------------------------------------------------------------------------------------------
+# on-device sampler (include/ufair.h "on-device ensemble sampler")
+# ------------------------------------------------------------------------------------------------
+def sampler_tables(gases=GASES, *, dense_pools: bool = False):
+    """The perturbed-parameter recipe of :func:`sample_params` as sampler tables:
+    dict(gas_base [G][17], gas_sigma, gas_dist, thermal_base [4], thermal_sigma, thermal_dist,
+    e_scale_sigma) -- tau, a, r0, f, q, d lognormal(0.1); rU, rT, rA normal(1, 0.13); C0 and the
+    emission-to-concentration factor fixed; emission scale normal(1, 0.05)."""
+
+    class _Zero:  # the unperturbed table: sample_params with every normal draw = 0
+        def standard_normal(self, shape):
+            return np.zeros(shape)
+
+    gp, tp = sample_params(1, _Zero(), gases, dense_pools=dense_pools)
+    G = len(gases)
+    dist = np.zeros((G, _abi.GP_COUNT), dtype=np.uint8)
+    sigma = np.zeros((G, _abi.GP_COUNT))
+    for rows, d, s in (((_abi.GP_A0, _abi.GP_A0 + 8), _abi.DIST_LOGNORMAL, 0.1),      # a_1..4, tau_1..4
+                       ((_abi.GP_R0, _abi.GP_R0 + 1), _abi.DIST_LOGNORMAL, 0.1),
+                       ((_abi.GP_RU, _abi.GP_RA + 1), _abi.DIST_NORMAL, 0.13),
+                       ((_abi.GP_F1, _abi.GP_F3 + 1), _abi.DIST_LOGNORMAL, 0.1)):
+        dist[:, rows[0]:rows[1]] = d
+        sigma[:, rows[0]:rows[1]] = s
+    return dict(gas_base=np.ascontiguousarray(gp[:, :, 0]), gas_sigma=sigma, gas_dist=dist,
+                thermal_base=np.ascontiguousarray(tp[:, 0]), thermal_sigma=np.full(_abi.TP_COUNT, 0.1),
+                thermal_dist=np.full(_abi.TP_COUNT, _abi.DIST_LOGNORMAL, dtype=np.uint8), e_scale_sigma=0.05)
+
+
+def sample_on_device(n_member: int, seed: int, *, first_member: int = 0, n_scen: int = 4, tables=None, gases=GASES,
+                     dense_pools: bool = False, precision: str = "f64", device=None):
+    """Members first_member .. first_member + n_member - 1 of the (seed, tables) ensemble, generated
+    on the GPU: (gas_params [G][17][M], thermal_params [4][M], e_scale [G][M], scen_idx [M] int32)
+    as CUDA tensors.  A member's values depend only on the seed and its global index, so ranks that
+    take consecutive member blocks hold exactly the ensemble a single call would produce."""
+    import ctypes as C
+
+    import torch
+    if not torch.cuda.is_available():
+        raise RuntimeError("fiveeqscm_b200 needs a CUDA device (B200, sm_100a); there is no CPU fallback")
+    t = tables if tables is not None else sampler_tables(gases, dense_pools=dense_pools)
+    G = int(np.asarray(t["gas_base"]).shape[0])
+    sp = _abi.UfairSampler(n_gas=G, seed=int(seed) & (2 ** 64 - 1), n_scen=int(n_scen),
+                           e_scale_sigma=float(t["e_scale_sigma"]))
+    for g in range(G):
+        for r in range(_abi.GP_COUNT):
+            sp.gas_base[g][r] = float(t["gas_base"][g][r])
+            sp.gas_sigma[g][r] = float(t["gas_sigma"][g][r])
+            sp.gas_dist[g][r] = int(t["gas_dist"][g][r])
+    for k in range(_abi.TP_COUNT):
+        sp.thermal_base[k], sp.thermal_sigma[k] = float(t["thermal_base"][k]), float(t["thermal_sigma"][k])
+        sp.thermal_dist[k] = int(t["thermal_dist"][k])
+    dev = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+    dtype = torch.float64 if precision == "f64" else torch.float32
+    M = int(n_member)
+    ld = (M + 3) // 4 * 4                                   # 16-byte rows in either precision
+    gp = torch.empty(G, _abi.GP_COUNT, ld, dtype=dtype, device=dev)
+    tp = torch.empty(_abi.TP_COUNT, ld, dtype=dtype, device=dev)
+    esc = torch.empty(G, ld, dtype=dtype, device=dev)
+    scen = torch.empty(max(M, 1), dtype=torch.int32, device=dev)
+    if ld != M:
+        gp.zero_(); tp.zero_(); esc.zero_()
+    fn = _abi.lib().ufair_sample_f64 if precision == "f64" else _abi.lib().ufair_sample_f32
+    with torch.cuda.device(dev):
+        _abi.check(fn(C.byref(sp), int(first_member), M, ld, gp.data_ptr(), tp.data_ptr(), esc.data_ptr(),
+                      scen.data_ptr(), torch.cuda.current_stream(dev).cuda_stream))
+    return gp[..., :M], tp[..., :M], esc[..., :M], scen[:M]

@@ -224,6 +224,46 @@ int ufair_g1g0_f64(const double* a, const double* tau, int64_t n_member, int64_t
 int ufair_kq_f64(const double* tcr, const double* ecs, const double* d1, const double* d2,
                  double f2x, int64_t n_member, double* q1, double* q2, void* stream);
 
+/* ---- on-device ensemble sampler (parameter / scenario sampling next to the path) ----
+ * Fills gas_params, thermal_params, e_scale and scen_idx for members first_member ..
+ * first_member + n_member - 1 of the ensemble that (sampler, seed) defines.  A member's values
+ * depend only on the seed and its GLOBAL index, so any split of the member axis over calls or GPUs
+ * yields the same ensemble, bit for bit.
+ *
+ * Random stream (counter-based, Philox4x32-10 of Salmon et al. 2011; key = seed low, seed high;
+ * counter = member low, member high, block, 0x55464152):  the four output words x0..x3 give
+ *   u_a = (((x1 << 32 | x0) >> 11) + 0.5) 2^-53,  u_b likewise from x3, x2          (both in (0, 1))
+ *   z_even = sqrt(-2 ln u_a) cos(2 pi u_b),  z_odd = sqrt(-2 ln u_a) sin(2 pi u_b)  (Box-Muller)
+ * and slot s of a member is z_{s & 1} of block s >> 1.  Slots: gas g row r -> 18 g + r;
+ * e_scale[g] -> 18 g + 17; thermal row k -> 72 + k; scen_idx = (x0 of block 38 * n_scen) >> 32.
+ * A row with distribution UFAIR_DIST_LOGNORMAL is base * exp(sigma z), UFAIR_DIST_NORMAL is
+ * base * (1 + sigma z), UFAIR_DIST_FIXED is base; the four pool fractions of a gas are then
+ * renormalised to sum 1; e_scale = 1 + e_scale_sigma z.  Everything is evaluated in double; the
+ * _f32 entry point rounds once on store.  Output pointers may be NULL (that array is skipped). */
+enum { UFAIR_DIST_FIXED = 0, UFAIR_DIST_LOGNORMAL = 1, UFAIR_DIST_NORMAL = 2 };
+
+typedef struct ufair_sampler {
+  uint32_t struct_size; /* = sizeof(ufair_sampler); checked */
+  int32_t n_gas;
+  uint64_t seed;
+  int32_t n_scen;       /* scen_idx in [0, n_scen) */
+  int32_t reserved;
+  double e_scale_sigma;
+  double gas_base[UFAIR_MAX_GAS][UFAIR_GP_COUNT];
+  double gas_sigma[UFAIR_MAX_GAS][UFAIR_GP_COUNT];
+  double thermal_base[UFAIR_TP_COUNT];
+  double thermal_sigma[UFAIR_TP_COUNT];
+  uint8_t gas_dist[UFAIR_MAX_GAS][24]; /* UFAIR_DIST_* per row (first UFAIR_GP_COUNT entries used) */
+  uint8_t thermal_dist[8];             /* first UFAIR_TP_COUNT entries used */
+} ufair_sampler;
+
+int ufair_sample_f64(const ufair_sampler* s, int64_t first_member, int64_t n_member, int64_t ld_member,
+                     double* gas_params, double* thermal_params, double* e_scale, int32_t* scen_idx,
+                     void* stream);
+int ufair_sample_f32(const ufair_sampler* s, int64_t first_member, int64_t n_member, int64_t ld_member,
+                     float* gas_params, float* thermal_params, float* e_scale, int32_t* scen_idx,
+                     void* stream);
+
 /* ---- the one function the reference ships (U_FaIR/concentrations.py:4-5) ----
  * out[i] = e0[i] * exp(-time[i]) over n already-broadcast elements. */
 int ufair_hfc_pulse_f64(const double* e0, const double* time, double* out, int64_t n, void* stream);

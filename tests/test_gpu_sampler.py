@@ -1,0 +1,83 @@
+"""On-device ensemble sampler against its numpy restatement: the integer stream and
+the scenario indices bit-exact, the floating-point transforms to a few ulp, sharding invariance, and
+an end-to-end run from sampled parameters."""
+import numpy as np
+import pytest
+
+from fiveeqscm_b200 import _abi
+from fiveeqscm_b200 import params as P
+from oracle import c_oracle as co
+from oracle import ufair_oracle as o
+from tests.util import field_relerr, to_dev, to_np
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def api():
+    import torch
+    assert torch.cuda.is_available()
+    from fiveeqscm_b200 import concentrations as c
+    _abi.lib()
+    return c
+
+
+def _close(got, ref, rtol):
+    got, ref = np.asarray(got, dtype=np.float64), np.asarray(ref, dtype=np.float64)
+    return bool(np.all(np.abs(got - ref) <= rtol * np.abs(ref)))
+
+
+@pytest.mark.parametrize("dense,gases", [(False, P.GASES), (True, P.GASES), (False, ("co2", "ch4", "n2o", "hfc")), (False, ("hfc",))])
+def test_device_sampler_matches_oracle(api, dense, gases):
+    M, seed, first = 10_007, 20261018, 123_456_789_012     # global indices beyond 2^32: high counter word in use
+    t = P.sampler_tables(gases, dense_pools=dense)
+    gp, tp, esc, scen = P.sample_on_device(M, seed, first_member=first, tables=t)
+    rgp, rtp, resc, rscen = o.sample_ensemble(seed, first, M, n_scen=4, **t)
+    assert np.array_equal(to_np(scen), rscen)                                   # integer path: bit-exact
+    assert _close(to_np(gp), rgp, 1e-14) and _close(to_np(tp), rtp, 1e-14) and _close(to_np(esc), resc, 1e-14)
+    assert np.array_equal(to_np(gp)[:, _abi.GP_C0], rgp[:, _abi.GP_C0])         # fixed rows: the table, exactly
+    assert np.array_equal(to_np(gp) == 0.0, rgp == 0.0)                         # absent pools / terms stay absent
+
+
+def test_sharding_invariance_and_fp32(api):
+    import torch
+    t = P.sampler_tables()
+    whole = P.sample_on_device(5000, 99, tables=t)
+    parts = [P.sample_on_device(n, 99, first_member=f, tables=t) for f, n in ((0, 1234), (1234, 2001), (3235, 1765))]
+    for k in range(4):
+        assert torch.equal(torch.cat([p[k] for p in parts], dim=-1), whole[k])
+    f32 = P.sample_on_device(5000, 99, tables=t, precision="f32")
+    for k in range(3):
+        assert f32[k].dtype == torch.float32 and torch.equal(f32[k], whole[k].to(torch.float32))   # rounded once, on store
+    assert torch.equal(f32[3], whole[3])
+
+
+def test_run_from_sampled_ensemble_matches_oracle(api):
+    """Sampler -> integrator on the device (scenario-shared emissions: nothing per-member ever crosses
+    PCIe) against oracle sampler -> oracle integrator."""
+    import torch
+    M, n_t, seed = 3000, 200, 5
+    t = P.sampler_tables()
+    scen_E = P.scenario_emissions(n_t)
+    gp, tp, esc, scen = P.sample_on_device(M, seed, tables=t)
+    res = api.run_ensemble(to_dev(scen_E), gp, tp, scen_idx=scen, e_scale=esc)
+    torch.cuda.synchronize()
+    rgp, rtp, resc, rscen = o.sample_ensemble(seed, 0, M, n_scen=4, **t)
+    ref = co.oxfair(scen_E, rgp, rtp, scen_idx=rscen, e_scale=resc)
+    for k in ("C", "RF", "T"):
+        assert field_relerr(to_np(getattr(res, k)), ref[k]) < 1e-10, k
+
+
+def test_sampler_argument_errors(api):
+    import ctypes as C
+    L = _abi.lib()
+    sp = _abi.UfairSampler(n_gas=3, n_scen=4)
+    assert L.ufair_sample_f64(C.byref(sp), 0, 0, 0, None, None, None, None, None) == _abi.OK      # empty: no launch
+    assert L.ufair_sample_f64(C.byref(sp), -1, 4, 4, None, None, None, None, None) == _abi.ERR_ARG
+    sp.n_scen = 0
+    assert L.ufair_sample_f64(C.byref(sp), 0, 4, 4, None, None, None, None, None) == _abi.ERR_ARG
+    sp.n_scen, sp.struct_size = 4, 8
+    assert L.ufair_sample_f64(C.byref(sp), 0, 4, 4, None, None, None, None, None) == _abi.ERR_ARG
+    bad = _abi.UfairSampler(n_gas=2, n_scen=1)
+    bad.gas_dist[1][3] = 7
+    assert L.ufair_sample_f64(C.byref(bad), 0, 4, 4, None, None, None, None, None) == _abi.ERR_ARG
