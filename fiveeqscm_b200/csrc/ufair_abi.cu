@@ -417,17 +417,21 @@ __global__ void hfc_pulse_kernel(const double* e0, const double* time, double* o
 // ---- device-math probe (tests/test_gpu_math.py) ---------------------------------------------------
 template <typename Real> __global__ void math_probe_kernel(int op, const Real* x, Real* y, long long n) {
   using M = Math<Real>;
+  __shared__ __align__(16) unsigned char tbl[512];  // the exponential table, as the integrator's warps hold it
+  const uint32_t tb = (uint32_t)__cvta_generic_to_shared(tbl);
+  if (threadIdx.x < 32) M::fill_table(tb, (int)threadIdx.x);
+  __syncthreads();
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   const Real v = x[i];
   Real r;
   switch (op) {
-    case 0: r = M::decay(v); break;
-    case 1: r = M::exp_(v); break;
+    case 0: r = M::decay(v, tb); break;
+    case 1: r = M::exp_(v, tb); break;
     case 2: r = M::rcp(v); break;
     case 3: r = M::sqrt_(v); break;
     case 4: r = M::log_(v); break;
-    default: r = M::sinh_pair(v); break;
+    default: r = M::sinh_pair(v, tb); break;
   }
   y[i] = r;
 }

@@ -73,6 +73,12 @@
 #ifndef UFAIR_MINB_F32_FORM
 #define UFAIR_MINB_F32_FORM 16
 #endif
+// experiment: which per-lane constants live in REGISTERS instead of shared memory (bit 0: the five
+// alpha_val constants, bit 1: the eight pool constants, bit 2: the four thermal constants).  Fewer
+// LDS wavefronts against more registers (pair with a lower UFAIR_MINB_F64).
+#ifndef UFAIR_REGCONST
+#define UFAIR_REGCONST 0
+#endif
 #ifndef UFAIR_TT
 #define UFAIR_TT 8  // time steps per shared-memory tile (8 measured ~2 % faster than 4)
 #endif
@@ -232,7 +238,7 @@ constexpr size_t round128(size_t b) { return (b + 127) / 128 * 128; }
 // per-WARP shared memory, in bytes (every piece 128-byte aligned: tensor-map TMA destinations)
 template <typename Real, int NGAS, int AMODE, int GPL_> struct WarpSmem {
   static constexpr int GPL = GPL_;
-  static constexpr bool HOT_SMEM = (GPL == 1) || sizeof(Real) == 8;
+  static constexpr bool HOT_SMEM = ((GPL == 1) || sizeof(Real) == 8) && !(sizeof(Real) == 8 && (UFAIR_REGCONST & 1));
   static constexpr int MW = members_per_warp(sizeof(Real), NGAS, GPL);
   static constexpr int G_HOT = G_COLD;                            // first hot row (if in smem)
   static constexpr int G_X0 = G_COLD + (HOT_SMEM ? H_COUNT : 0);  // SINH: g0; NEWTON: g1, ln g0, 1/c
@@ -249,7 +255,9 @@ template <typename Real, int NGAS, int AMODE, int GPL_> struct WarpSmem {
   static __host__ __device__ constexpr uint32_t off_par(bool fx_member) {
     return off_f + (fx_member ? kStages * f_stage : 0u);
   }
-  static __host__ __device__ constexpr uint32_t off_bar(bool fx_member) { return off_par(fx_member) + par_bytes; }
+  static constexpr uint32_t tbl_bytes = sizeof(Real) == 8 ? kExpTableBytes : 0u;  // exp table copy (ufair_math.cuh)
+  static __host__ __device__ constexpr uint32_t off_tbl(bool fx_member) { return off_par(fx_member) + par_bytes; }
+  static __host__ __device__ constexpr uint32_t off_bar(bool fx_member) { return off_tbl(fx_member) + tbl_bytes; }
   static __host__ __device__ constexpr uint32_t bytes(bool fx_member) { return off_bar(fx_member) + 128u; }
 };
 
@@ -311,9 +319,12 @@ __global__ void __launch_bounds__(kWarps * 32, min_blocks(sizeof(Real), NGAS, GP
   uint32_t f_addr = wbase + WS::off_f + (uint32_t)i * ES;
   uint32_t par = wbase + WS::off_par(fx_member) + (uint32_t)lane * ES;       // this lane's parameter column
   const uint32_t bar0 = wbase + WS::off_bar(fx_member);
+  uint32_t tb = wbase + WS::off_tbl(fx_member);  // this warp's copy of the exponential table
+  M::fill_table(tb, lane);
   pin(e_addr);
   pin(f_addr);
   pin(par);
+  pin(tb);
 #define PARG(gl, k) lds(par + (uint32_t)((gl) * WS::PG + (k)) * 32u * ES, Real())
 #define SETG(gl, k, v) sts(par + (uint32_t)((gl) * WS::PG + (k)) * 32u * ES, (Real)(v))
 #define PART(k) lds(par + (uint32_t)(GPL * WS::PG + (k)) * 32u * ES, Real())
@@ -427,6 +438,20 @@ __global__ void __launch_bounds__(kWarps * 32, min_blocks(sizeof(Real), NGAS, GP
   }
   Real Ssum = S0 + S1;  // carried so that the mid-step mean costs one add
   __syncwarp();
+  constexpr bool POOL_REG = sizeof(Real) == 8 && (UFAIR_REGCONST & 2), THERM_REG = sizeof(Real) == 8 && (UFAIR_REGCONST & 4);
+  Real rK0[GPL][4], rKA[GPL][4], rT[T_COUNT];  // dead unless the experiment switches ask for them
+#pragma unroll
+  for (int gl = 0; gl < GPL; ++gl)
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      rK0[gl][q] = (POOL_REG && q < form_pools(FORM, gl)) ? PARG(gl, G_K0 + q) : Real(0);
+      rKA[gl][q] = (POOL_REG && q < form_pools(FORM, gl)) ? PARG(gl, G_KA0 + q) : Real(0);
+    }
+#pragma unroll
+  for (int k = 0; k < T_COUNT; ++k) rT[k] = THERM_REG ? PART(k) : Real(0);
+#define PK0(gl, q) (POOL_REG ? rK0[gl][q] : PARG(gl, G_K0 + (q)))
+#define PKA(gl, q) (POOL_REG ? rKA[gl][q] : PARG(gl, G_KA0 + (q)))
+#define PTH(k) (THERM_REG ? rT[k] : PART(k))
 
   const int scen = (a.scen_idx != nullptr) ? a.scen_idx[m] : 0;
   const Real dt = (Real)a.dt;
@@ -503,7 +528,7 @@ __global__ void __launch_bounds__(kWarps * 32, min_blocks(sizeof(Real), NGAS, GP
           const Real umax = HOT_SMEM ? PARG(gl, WS::G_HOT + H_UMAX) : hot[gl][H_UMAX];
           u = (u > umax) ? umax : u;
         }
-        alpha = (AMODE == UFAIR_ALPHA_SINH) ? PARG(gl, WS::G_X0) * M::sinh_pair(u) : M::exp_(u);
+        alpha = (AMODE == UFAIR_ALPHA_SINH) ? PARG(gl, WS::G_X0) * M::sinh_pair(u, tb) : M::exp_(u, tb);
         if (AMODE == UFAIR_ALPHA_NEWTON) {
           const Real iirf = (u - PARG(gl, WS::G_X0 + 1)) * PARG(gl, WS::G_X0);
           const Real invc = PARG(gl, WS::G_X0 + 2);
@@ -512,9 +537,9 @@ __global__ void __launch_bounds__(kWarps * 32, min_blocks(sizeof(Real), NGAS, GP
             Real f = -iirf, fp = 0;
 #pragma unroll
             for (int q = 0; q < NP; ++q) {
-              const Real z = PARG(gl, G_K0 + q) * hdt * ia;
-              const Real mz = M::decay(z);
-              const Real at = PARG(gl, G_KA0 + q) * invc;  // a_i tau_i
+              const Real z = PK0(gl, q) * hdt * ia;
+              const Real mz = M::decay(z, tb);
+              const Real at = PKA(gl, q) * invc;  // a_i tau_i
               f = fma(at * alpha, mz, f);
               fp = fma(at, mz - z * (Real(1) - mz), fp);
             }
@@ -528,7 +553,7 @@ __global__ void __launch_bounds__(kWarps * 32, min_blocks(sizeof(Real), NGAS, GP
       Real mq[4];
 #pragma unroll
       for (int q = 0; q < 4; ++q)
-        if (q < NP) mq[q] = (AMODE == UFAIR_ALPHA_ONE) ? PARG(gl, G_K0 + q) : M::decay(PARG(gl, G_K0 + q) * inva);
+        if (q < NP) mq[q] = (AMODE == UFAIR_ALPHA_ONE) ? PK0(gl, q) : M::decay(PK0(gl, q) * inva, tb);
       if (INV) {
         // concentration-driven gas: `e` is the target C; step_conc is linear in E, so
         //   E = (C_target - C0 - sum R_i (1 - m_i)) / (alpha sum m_i c a_i tau_i)
@@ -537,7 +562,7 @@ __global__ void __launch_bounds__(kWarps * 32, min_blocks(sizeof(Real), NGAS, GP
         for (int q = 0; q < 4; ++q)
           if (q < NP) {
             keep += fma(-mq[q], R[gl][q], R[gl][q]);
-            gain = fma(mq[q], PARG(gl, G_KA0 + q), gain);
+            gain = fma(mq[q], PKA(gl, q), gain);
           }
         const Real e_inv = ((e - PARG(gl, G_C0)) - keep) * M::rcp(gain * alpha);
         if ((a.conc_driven >> (g0 + gl)) & 1) e = e_inv;
@@ -546,7 +571,7 @@ __global__ void __launch_bounds__(kWarps * 32, min_blocks(sizeof(Real), NGAS, GP
       const Real ea = e * alpha;
 #pragma unroll
       for (int q = 0; q < 4; ++q)
-        if (q < NP) R[gl][q] = fma(mq[q], fma(ea, PARG(gl, G_KA0 + q), -R[gl][q]), R[gl][q]);
+        if (q < NP) R[gl][q] = fma(mq[q], fma(ea, PKA(gl, q), -R[gl][q]), R[gl][q]);
       Gcum[gl] = fma(e, dt, Gcum[gl]);
       sumR[gl] = sum_pools(R[gl], NP);
       const Real C = PARG(gl, G_C0) + sumR[gl];
@@ -574,8 +599,8 @@ __global__ void __launch_bounds__(kWarps * 32, min_blocks(sizeof(Real), NGAS, GP
       Ftot += fx;
     }
     // ---- step_temp (with GROUPS > 1 computed redundantly, bit-identically, by a member's lanes)
-    const Real s0 = fma(PART(T_QM0), Ftot, S0 * PART(T_DEC0));
-    const Real s1 = fma(PART(T_QM1), Ftot, S1 * PART(T_DEC1));
+    const Real s0 = fma(PTH(T_QM0), Ftot, S0 * PTH(T_DEC0));
+    const Real s1 = fma(PTH(T_QM1), Ftot, S1 * PTH(T_DEC1));
     const Real Snew = s0 + s1;
     const Real T = fma(wNew, Snew, wOld * Ssum);
     S0 = s0;
@@ -685,6 +710,9 @@ __global__ void __launch_bounds__(kWarps * 32, min_blocks(sizeof(Real), NGAS, GP
       so[(long long)(5 * NGAS + 2) * ld + m] = Tprev;
     }
   }
+#undef PK0
+#undef PKA
+#undef PTH
 #undef PARG
 #undef SETG
 #undef PART
