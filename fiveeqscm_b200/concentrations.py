@@ -175,6 +175,19 @@ def _with_E(outputs, conc_driven):
     return outputs + ("E",) if driven and "E" not in outputs else outputs
 
 
+def _detect_form_host(gp, state_in):
+    """gas_form from HOST parameter arrays: the numpy twin of ufair_detect_form_* (same rule)."""
+    out = []
+    for g in range(gp.shape[0]):
+        used = [bool(np.any(gp[g, _abi.GP_A0 + q] != 0) or (state_in is not None and np.any(state_in[5 * g + q] != 0)))
+                for q in range(1, 4)]
+        n_pool = 4 if used[2] else 3 if used[1] else 2 if used[0] else 1
+        terms = sum(bit for bit, row in ((_abi.TERM_LOG, _abi.GP_F1), (_abi.TERM_LIN, _abi.GP_F2),
+                                         (_abi.TERM_SQRT, _abi.GP_F3)) if np.any(gp[g, row] != 0))
+        out.append(_abi.form(n_pool, terms or _abi.TERM_LIN))
+    return out
+
+
 def _form_byte(f) -> int:
     """One gas_form entry: None / 0 (unspecified), a raw UFAIR_FORM byte, or (n_pool, "log+lin+sqrt")."""
     if f is None:
@@ -217,8 +230,7 @@ def run_ensemble(emissions, gas_params, thermal_params, *, dt=1.0, scen_idx=None
                    is diagnosed (step_conc inverted exactly) and returned as ``.E`` (all gases).
     gas_form       per-gas specialisation (include/ufair.h UFAIR_FORM): "auto" scans the parameters on
                    the device and lets the library skip pools with a_i == 0 and forcing terms whose
-                   coefficient is zero for every member (CUDA inputs; the host pipeline treats
-                   "auto" as None); None = no specialisation; or one entry per gas, e.g.
+                   coefficient is zero for every member; None = no specialisation; or one entry per gas, e.g.
                    [None, (1, "lin+sqrt"), (1, "lin+sqrt")] -- a promise the caller makes.
 
     torch.cuda tensors -> results are torch.cuda tensors (current stream, asynchronous);
@@ -462,6 +474,9 @@ def _run_host(torch, E, gp, tp, dt, scen_idx, e_scale, f_ext, fext_per_member, s
     E, gp, tp, e_scale, f_ext, state_in = (arr(x) for x in (E, gp, tp, e_scale, f_ext, state_in))
     fshape = None if f_ext is None else f_ext.shape
     G, n_t, M, e_scen, n_scen, fext_mode = _shapes(E.shape, gp.shape, tp.shape, scen_idx, fshape, fext_per_member)
+    auto_form = isinstance(gas_form, str)
+    if auto_form and gas_form != "auto":
+        raise ValueError("gas_form must be 'auto', None or one entry per gas")
     d = _build_desc(G, n_t, M, M, n_scen, e_scen, fext_mode, alpha_mode, newton_iters, t_mode, outputs, dt, iirf_h,
                     iirf_max, stats, gas_form, conc_driven)
     d.emissions, d.gas_params, d.thermal_params = E.ctypes.data, gp.ctypes.data, tp.ctypes.data
@@ -485,6 +500,9 @@ def _run_host(torch, E, gp, tp, dt, scen_idx, e_scale, f_ext, fext_per_member, s
         if state_in.shape != (_abi.state_rows(G), M):
             raise ValueError("state_in must be [5G+3][M]")
         d.state_in = state_in.ctypes.data
+    if auto_form and M:
+        for g, f in enumerate(_detect_form_host(gp, state_in)):
+            d.gas_form[g] = f
     res = out if out is not None else EnsembleResult()
     res.spec, res.n_member = stats, M
 

@@ -168,3 +168,57 @@ def test_gas_form_spelling_and_flop_convention():
     # the survey's 751 flops per member-step is the four-pool, three-term case of the per-form count
     assert bench.algorithmic_flops((0, 0, 0)) == bench.FLOPS_PER_STEP == 751.0
     assert bench.algorithmic_flops((0x14, 0x41, 0x41)) == 236 + 2 * 102 + 13
+
+
+def test_scenario_tables_and_summary_frames(tmp_path):
+    import pandas as pd
+    from fiveeqscm_b200 import frames
+    from fiveeqscm_b200 import params as P
+    from fiveeqscm_b200.concentrations import EnsembleResult, HistSpec
+    from oracle import ufair_oracle as o
+    n_t = 30
+    scen = P.scenario_emissions(n_t)                                            # [3][n_t][4]
+    rows = [dict(year=1765 + t, scenario=f"s{s}", co2=scen[0, t, s], ch4=scen[1, t, s], n2o=scen[2, t, s])
+            for s in (2, 0, 1) for t in reversed(range(n_t))]                   # shuffled on purpose
+    path = tmp_path / "scen.csv"
+    pd.DataFrame(rows).to_csv(path, index=False)
+    years, names, E, dt = frames.scenarios_from_csv(path)
+    assert names == ["s2", "s0", "s1"] and dt == 1.0 and np.array_equal(years, 1765.0 + np.arange(n_t))
+    assert np.allclose(E, scen[:, :, [2, 0, 1]], rtol=1e-15)
+    with pytest.raises(ValueError):
+        frames.scenarios_from_frame(pd.DataFrame(rows).drop(columns="ch4"))
+    with pytest.raises(ValueError):
+        frames.scenarios_from_frame(pd.DataFrame(rows[:-1]))                    # one scenario a year short
+    with pytest.raises(ValueError):
+        frames.scenarios_from_frame(pd.DataFrame([dict(year=y, co2=1, ch4=1, n2o=1) for y in (2000, 2001, 2003)]))
+    # summaries from an (oracle-made) result
+    gp, tp = P.sample_params(500, np.random.default_rng(0))
+    run = o.oxfair(E, gp, tp, scen_idx=np.arange(500) % 3)
+    spec = HistSpec(lo=-1.0, hi=4.0, bins=500)
+    hist, mom = o.temperature_stats(run["T"], spec.lo, spec.hi, spec.bins)
+    res = EnsembleResult(C=run["C"], RF=run["RF"], T=run["T"], hist=hist.astype(np.int64), moments=mom, spec=spec, n_member=500)
+    sf = frames.summary_frame(res, years, pcts=(5, 50, 95))
+    assert list(sf.columns) == ["year", "members", "T_mean", "T_std", "T_min", "T_max", "T_p5", "T_p50", "T_p95"]
+    assert np.allclose(sf["T_mean"], run["T"].mean(axis=1), atol=1e-12) and np.all(sf["members"] == 500)
+    assert np.all(sf["T_p5"] <= sf["T_p50"]) and np.all(sf["T_p50"] <= sf["T_p95"])
+    assert np.max(np.abs(sf["T_p50"] - np.median(run["T"], axis=1))) < 2 * (spec.hi - spec.lo) / spec.bins
+    mf = frames.member_frame(res, years, member=7)
+    assert np.array_equal(mf["C_co2"], run["C"][0, :, 7]) and np.array_equal(mf["T"], run["T"][:, 7]) and "E_co2" not in mf
+    with pytest.raises(ValueError):
+        frames.summary_frame(EnsembleResult(T=run["T"]), years)
+
+
+def test_host_side_form_detection_matches_the_device_rule():
+    from fiveeqscm_b200 import _abi
+    from fiveeqscm_b200 import params as P
+    from fiveeqscm_b200.concentrations import _detect_form_host
+    LOG, LIN, SQRT = _abi.TERM_LOG, _abi.TERM_LIN, _abi.TERM_SQRT
+    gp, _ = P.sample_params(64, np.random.default_rng(1), ("co2", "ch4", "n2o", "hfc"))
+    assert _detect_form_host(gp, None) == [_abi.form(4, LOG), _abi.form(1, SQRT), _abi.form(1, SQRT), _abi.form(1, LIN)]
+    st = np.zeros((_abi.state_rows(4), 64))
+    st[5 * 2 + 1, 3] = 1e-9                                  # N2O pool 2 carries mass in one member
+    assert _detect_form_host(gp, st)[2] == _abi.form(2, SQRT)
+    gpd, _ = P.sample_params(8, np.random.default_rng(1), dense_pools=True)
+    assert _detect_form_host(gpd, None) == [_abi.form(4, LOG | LIN | SQRT)] * 3
+    gp0 = np.array(gp[3:4]); gp0[0, _abi.GP_F2] = 0.0       # no forcing at all: the linear term stands in
+    assert _detect_form_host(gp0, None) == [_abi.form(1, LIN)]
