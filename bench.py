@@ -287,7 +287,7 @@ def main():
         plan.launch()                      # the fused integrator (+ in-loop histogram): the dominant kernel
         if i is not None:
             kern_ev[i][1].record()
-        plan.moments()                     # second statistics pass over the T rows
+        plan.stats_pass()                     # second statistics pass over the T rows
         plan.finalize_stats()
         if world > 1 and spec is not None:
             D.allreduce_stats(res.hist, res.moments)

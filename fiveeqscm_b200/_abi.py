@@ -146,8 +146,8 @@ SIGNATURES = {
     "ufair_kernel_variant": (C.c_int, [C.POINTER(UfairDesc), _i32, C.POINTER(C.c_uint32), C.POINTER(_i32),
                                        C.POINTER(_i32)]),
     "ufair_stats_reset": (C.c_int, [C.POINTER(UfairDesc), _vp]),
-    "ufair_stats_moments_f64": (C.c_int, [C.POINTER(UfairDesc), _vp]),
-    "ufair_stats_moments_f32": (C.c_int, [C.POINTER(UfairDesc), _vp]),
+    "ufair_stats_pass_f64": (C.c_int, [C.POINTER(UfairDesc), _vp]),
+    "ufair_stats_pass_f32": (C.c_int, [C.POINTER(UfairDesc), _vp]),
     "ufair_stats_finalize": (C.c_int, [C.POINTER(UfairDesc), _vp, _vp, _vp]),
     "ufair_hist_percentiles": (C.c_int, [_vp, _i32, _i32, _dbl, _dbl, _vp, _i32, _vp, _vp]),
     "ufair_g1g0_f64": (C.c_int, [_vp, _vp, _i64, _i64, _dbl, _i32, _vp, _vp, _vp]),

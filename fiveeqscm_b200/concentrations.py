@@ -409,10 +409,10 @@ class DevicePlan:
         """One launch of the fused integrator on the current stream (asynchronous)."""
         _abi.check(self._run(C.byref(self.desc), self._stream()))
 
-    def moments(self):
-        """Second statistics pass: fold the T rows the integrator just wrote into the moments."""
+    def stats_pass(self):
+        """Statistics pass: histogram and moments of the T rows the integrator just wrote."""
         if self.stats is not None:
-            fn = self._L.ufair_stats_moments_f64 if self.precision == "f64" else self._L.ufair_stats_moments_f32
+            fn = self._L.ufair_stats_pass_f64 if self.precision == "f64" else self._L.ufair_stats_pass_f32
             _abi.check(fn(C.byref(self.desc), self._stream()))
 
     def finalize_stats(self):
@@ -425,7 +425,7 @@ class DevicePlan:
         with _torch().cuda.device(self.device):
             self.reset_stats()
             self.launch()
-            self.moments()
+            self.stats_pass()
             self.finalize_stats()
         return self.result
 

@@ -106,13 +106,6 @@ template <typename Real> static KArgs<Real> make_args(const ufair_desc* d) {
   a.oE = (Real*)d->out_E;
   a.conc_driven = d->conc_driven;
   a.state_out = (Real*)d->state_out;
-  a.hist_bins = d->hist_bins;
-  a.hist_copies = d->hist_copies;
-  a.hist_t0 = d->hist_t0;
-  a.hist_rows = d->hist_rows;
-  a.hist_lo = (Real)d->hist_lo;
-  a.hist_invw = d->stats ? (Real)((Real)d->hist_bins / ((Real)d->hist_hi - (Real)d->hist_lo)) : (Real)0;
-  a.hist = d->hist_private;
   return a;
 }
 
@@ -175,23 +168,68 @@ static int dispatch_mode(const ufair_desc* d, const KArgs<Real>& a, cudaStream_t
   }
 }
 
-// ---- moments of T: second pass over the T rows the integrator just wrote ---------------------------
-// CTA (c, t) folds member slice c of row t in a fixed order (strided per-thread partials, shuffle
-// tree, warps in order) and merges it into moments_private[c][hist_t0 + t]: no atomics, deterministic.
+// ---- statistics of T: second pass over the T rows the integrator just wrote ----------------------
+// CTA (c, t) handles member slice c of row t.
+//   histogram: bin = clamp(floor((T - lo) * invw), 0, bins - 1) in the run's precision (subtract and
+//   multiply rounded separately, NaN not counted); counts go to a shared-memory histogram (per-thread
+//   run-length merging in front of the atomics), then are added to hist_private[c][hist_t0 + t] -- a
+//   row this CTA alone owns, so no global atomics.  With more bins than fit in shared memory the counts go
+//   straight to that row with global atomics.
+//   moments: strided per-thread partials, shuffle tree, warps in order, merged into
+//   moments_private[c][hist_t0 + t]: no atomics, deterministic.
+constexpr int kStatsThreads = 256;
+constexpr int kStatsSmemBins = 16384;  // 64 KB of dynamic shared memory at most
+
 template <typename Real>
-__global__ void __launch_bounds__(256)
-    moments_pass_kernel(const Real* __restrict__ T, long long ld, long long n_member, int t0_row, int rows, double* mp) {
+__global__ void __launch_bounds__(kStatsThreads)
+    stats_pass_kernel(const Real* __restrict__ T, long long ld, long long n_member, int t0_row, int rows, int bins,
+                      Real lo, Real invw, int smem_hist, unsigned int* __restrict__ hp, double* mp) {
+  using M = Math<Real>;
+  extern __shared__ unsigned int sh[];
   const int c = blockIdx.x, copies = gridDim.x, t = blockIdx.y;
-  const long long lo = n_member * c / copies, hi = n_member * (c + 1) / copies;
+  const long long m_lo = n_member * c / copies, m_hi = n_member * (c + 1) / copies;
   const Real* row = T + (long long)t * ld;
+  unsigned int* grow = hp + ((size_t)c * rows + t0_row + t) * bins;
+  if (smem_hist) {
+    for (int b = threadIdx.x; b < bins; b += blockDim.x) sh[b] = 0u;
+    __syncthreads();
+  }
+  unsigned int* hdst = smem_hist ? sh : grow;
+  const int bins_m1 = bins - 1;
   double sm = 0.0, ss = 0.0, mn = INFINITY, mx = -INFINITY;
-  for (long long m = lo + threadIdx.x; m < hi; m += blockDim.x) {
-    const double v = (double)__ldcs(row + m);
+  // four independent streaming loads in flight per thread; counts are run-length merged per thread
+  // (a thread flushes one atomic when its bin changes), so a row whose members sit in one or two bins
+  // issues almost no atomics and a spread-out row issues conflict-free ones
+  const long long span = m_hi - m_lo;
+  int last = -1;
+  unsigned run = 0;
+  auto take = [&](Real x) {
+    const double v = (double)x;
     sm += v;
     ss = fma(v, v, ss);
     mn = fmin(mn, v);
     mx = fmax(mx, v);
+    const Real q = M::bin_x(x, lo, invw);
+    const int b = (q == q) ? max(0, min(bins_m1, M::floor_to_int(q))) : -1;
+    if (b != last) {
+      if (run) atomicAdd(hdst + last, run);
+      last = b;
+      run = 0;
+    }
+    run += (b >= 0);
+  };
+  const Real* src = row + m_lo;
+  long long k = threadIdx.x;
+  for (; k + 3 * kStatsThreads < span; k += 4 * kStatsThreads) {
+    const Real x0 = __ldcs(src + k), x1 = __ldcs(src + k + kStatsThreads), x2 = __ldcs(src + k + 2 * kStatsThreads),
+               x3 = __ldcs(src + k + 3 * kStatsThreads);
+    take(x0);
+    take(x1);
+    take(x2);
+    take(x3);
   }
+  for (; k < span; k += kStatsThreads) take(__ldcs(src + k));
+  if (run) atomicAdd(hdst + last, run);
 #pragma unroll
   for (int off = 16; off > 0; off >>= 1) {
     sm += __shfl_xor_sync(0xffffffffu, sm, off);
@@ -199,7 +237,7 @@ __global__ void __launch_bounds__(256)
     mn = fmin(mn, __shfl_xor_sync(0xffffffffu, mn, off));
     mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, off));
   }
-  __shared__ double red[8][4];
+  __shared__ double red[kStatsThreads / 32][4];
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   if (lane == 0) {
     red[w][0] = sm;
@@ -208,6 +246,9 @@ __global__ void __launch_bounds__(256)
     red[w][3] = mx;
   }
   __syncthreads();
+  if (smem_hist)
+    for (int b = threadIdx.x; b < bins; b += blockDim.x)
+      if (sh[b]) grow[b] += sh[b];
   if (threadIdx.x == 0) {
     double* o = mp + ((size_t)c * rows + t0_row + t) * UFAIR_MOM_COUNT;
     sm = o[UFAIR_MOM_SUM];
@@ -286,19 +327,28 @@ template <typename Real> int detect_form(const ufair_desc* d, int32_t* scratch, 
   return UFAIR_OK;
 }
 
-template <typename Real> int run_moments(const ufair_desc* d, cudaStream_t stream) {
+template <typename Real> int run_stats_pass(const ufair_desc* d, cudaStream_t stream) {
   int rc = validate_desc(d, sizeof(Real));
   if (rc != UFAIR_OK) return rc;
-  if (!d->stats) return set_error(UFAIR_ERR_ARG, "ufair_stats_moments: descriptor has stats == 0");
+  if (!d->stats) return set_error(UFAIR_ERR_ARG, "ufair_stats_pass: descriptor has stats == 0");
   if (d->n_member == 0 || d->n_t == 0) return UFAIR_OK;
-  moments_pass_kernel<Real><<<dim3((unsigned)d->hist_copies, (unsigned)d->n_t), 256, 0, stream>>>(
-      (const Real*)d->out_T, d->ld_member, d->n_member, d->hist_t0, d->hist_rows, d->moments_private);
-  cudaError_t e = cudaGetLastError();
-  if (e != cudaSuccess) return cuda_error(e, "moments_pass_kernel launch");
+  const int smem_hist = d->hist_bins <= kStatsSmemBins ? 1 : 0;
+  const size_t smem = smem_hist ? (size_t)d->hist_bins * sizeof(unsigned int) : 0;
+  cudaError_t e = cudaSuccess;
+  if (smem > 48 * 1024)
+    e = cudaFuncSetAttribute(stats_pass_kernel<Real>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return cuda_error(e, "cudaFuncSetAttribute(stats_pass_kernel)");
+  const Real lo = (Real)d->hist_lo;
+  const Real invw = (Real)((Real)d->hist_bins / ((Real)d->hist_hi - (Real)d->hist_lo));
+  stats_pass_kernel<Real><<<dim3((unsigned)d->hist_copies, (unsigned)d->n_t), kStatsThreads, smem, stream>>>(
+      (const Real*)d->out_T, d->ld_member, d->n_member, d->hist_t0, d->hist_rows, d->hist_bins, lo, invw, smem_hist,
+      d->hist_private, d->moments_private);
+  e = cudaGetLastError();
+  if (e != cudaSuccess) return cuda_error(e, "stats_pass_kernel launch");
   return UFAIR_OK;
 }
-template int run_moments<double>(const ufair_desc*, cudaStream_t);
-template int run_moments<float>(const ufair_desc*, cudaStream_t);
+template int run_stats_pass<double>(const ufair_desc*, cudaStream_t);
+template int run_stats_pass<float>(const ufair_desc*, cudaStream_t);
 template int run_device<double>(const ufair_desc*, cudaStream_t);
 template int run_device<float>(const ufair_desc*, cudaStream_t);
 
@@ -504,8 +554,8 @@ int64_t ufair_block_members(void) { return kWarps * 32; }
 int ufair_run_f64(const ufair_desc* d, void* stream) { return run_device<double>(d, (cudaStream_t)stream); }
 int ufair_run_f32(const ufair_desc* d, void* stream) { return run_device<float>(d, (cudaStream_t)stream); }
 
-int ufair_stats_moments_f64(const ufair_desc* d, void* stream) { return run_moments<double>(d, (cudaStream_t)stream); }
-int ufair_stats_moments_f32(const ufair_desc* d, void* stream) { return run_moments<float>(d, (cudaStream_t)stream); }
+int ufair_stats_pass_f64(const ufair_desc* d, void* stream) { return run_stats_pass<double>(d, (cudaStream_t)stream); }
+int ufair_stats_pass_f32(const ufair_desc* d, void* stream) { return run_stats_pass<float>(d, (cudaStream_t)stream); }
 
 int ufair_detect_form_f64(const ufair_desc* d, int32_t* scratch, uint8_t* form, void* stream) {
   return detect_form<double>(d, scratch, form, (cudaStream_t)stream);

@@ -152,7 +152,7 @@ static int run_chunks(ufair_workspace* ws, const ufair_desc* h, const ufair_desc
     k.out_E = S.b[B_OE].p;
     k.state_out = h->state_out ? S.b[B_SOUT].p : nullptr;
     rc = run_device<Real>(&k, ws->s_run);
-    if (rc == UFAIR_OK && h->stats) rc = run_moments<Real>(&k, ws->s_run);
+    if (rc == UFAIR_OK && h->stats) rc = run_stats_pass<Real>(&k, ws->s_run);
     if (rc != UFAIR_OK) return rc;
     CK(cudaEventRecord(S.run_done, ws->s_run), "cudaEventRecord");
     // ---- D2H

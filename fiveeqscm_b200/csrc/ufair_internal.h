@@ -9,5 +9,5 @@ int set_error(int code, const char* fmt, ...);
 int cuda_error(cudaError_t e, const char* what);
 int validate_desc(const ufair_desc* d, size_t elem);
 template <typename Real> int run_device(const ufair_desc* d, cudaStream_t stream);
-template <typename Real> int run_moments(const ufair_desc* d, cudaStream_t stream);
+template <typename Real> int run_stats_pass(const ufair_desc* d, cudaStream_t stream);
 }  // namespace ufair

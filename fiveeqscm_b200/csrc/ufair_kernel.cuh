@@ -39,9 +39,11 @@
 //     Per-member external forcing rides the same way through a 2-D map.
 //   * C / RF / T are written straight from registers with streaming (st.global.cs) stores, one
 //     aligned 256-byte run per warp and row -- nothing is re-read.
-//   * optional statistics: the lane owning a member adds its T to the privatised per-step
-//     histogram (RED.ADD.U32) as it goes; moments come from a second, HBM-speed pass over the T
-//     rows (ufair_abi.cu), which is cheaper than in-loop cross-lane reductions and deterministic.
+//   * optional statistics: the per-step histogram and the moments both come from a second,
+//     HBM-speed pass over the T rows this kernel writes (stats_pass_kernel, ufair_abi.cu): block-level
+//     shared-memory histograms with warp-aggregated atomics.  Measured: the in-loop version (one
+//     RED.ADD.U32 per member-step + the binning arithmetic in every lane) cost 2 ms of the 38 ms launch,
+//     the extra work in the pass costs 0.3 ms.
 #pragma once
 #include <cuda.h>
 #include <cuda_runtime.h>
@@ -155,9 +157,6 @@ template <typename Real> struct KArgs {
   Real* oE;
   int conc_driven;  // bit g: gas g's input rows are target concentrations (INV kernels only)
   Real* state_out;
-  int hist_bins, hist_copies, hist_t0, hist_rows;
-  Real hist_lo, hist_invw;
-  unsigned int* hist;
 };
 
 // ---- PTX wrappers: mbarrier, tensor-map TMA, shared-space loads/stores with 32-bit addresses ----
@@ -464,10 +463,8 @@ __global__ void __launch_bounds__(kWarps * 32, min_blocks(sizeof(Real), NGAS, GP
 
   // output predicates packed in one register; running output pointers (gas g0; + gl * gstride)
   const bool owner = active && (g0 == 0);  // the lane that owns the member's T / histogram count
-  constexpr unsigned WM_STATS = 0x100u;
   unsigned wm = (active ? (unsigned)(a.out_mask & (UFAIR_OUT_C | UFAIR_OUT_RF | UFAIR_OUT_ALPHA | (INV ? UFAIR_OUT_E : 0))) : 0u) |
-                ((owner && ((a.out_mask & UFAIR_OUT_T) || a.stats)) ? (unsigned)UFAIR_OUT_T : 0u) |
-                ((owner && a.stats) ? WM_STATS : 0u);
+                ((owner && ((a.out_mask & UFAIR_OUT_T) || a.stats)) ? (unsigned)UFAIR_OUT_T : 0u);
   pin(wm);
   const long long gstride = (long long)n_t * ld;
   const long long o_gas = (long long)g0 * gstride + m_raw;
@@ -476,8 +473,6 @@ __global__ void __launch_bounds__(kWarps * 32, min_blocks(sizeof(Real), NGAS, GP
   const long long dA = a.oA - a.oC;  // the (diagnostic) alpha output is addressed relative to pC
   const long long dE = INV ? (a.oE - a.oC) : 0;  // and so is the emissions output
   Real* pT = a.oT + m_raw;
-  unsigned int* hrow = a.stats ? a.hist + ((size_t)(wg % a.hist_copies) * a.hist_rows + a.hist_t0) * a.hist_bins : nullptr;
-  const int bins_m1 = a.hist_bins - 1;
 
   // scenario-mode inputs: register prefetch one step ahead through the read-only path
   Real e_next[GPL], esc[GPL], fx_next = 0;
@@ -609,14 +604,6 @@ __global__ void __launch_bounds__(kWarps * 32, min_blocks(sizeof(Real), NGAS, GP
     Tprev = T;
     if (wm & UFAIR_OUT_T) st_stream(pT, T);
     pT += ld;
-    if (wm & WM_STATS) {  // owner lane of a real member: one histogram count
-      const Real x = M::bin_x(T, a.hist_lo, a.hist_invw);
-      if (x == x) {
-        const int b = max(0, min(bins_m1, M::floor_to_int(x)));
-        atomicAdd(hrow + b, 1u);
-      }
-    }
-    hrow += a.hist_bins;  // next step's histogram row (dangling but unused when stats are off)
 #ifdef UFAIR_EXP_PAD  // cost-model experiment: UFAIR_EXP_PAD extra integer (or FP64) instructions per step
     {
       uint32_t pad = wm;

@@ -148,12 +148,12 @@ typedef struct ufair_desc {
   /* ---- ensemble statistics (stats == 1) ----
    * bin(T) = clamp(floor((T - hist_lo) * (hist_bins / (hist_hi - hist_lo))), 0, hist_bins-1),
    * evaluated in the run's precision; NaN is not counted.
-   * The integrator adds into `hist_copies` private histogram copies (warp w -> copy
-   * w % hist_copies); the moments (sum, sum of squares, min, max of T over members) come from a
-   * second pass over the T rows the integrator wrote, so out_T must be non-NULL when stats == 1
-   * (whether or not UFAIR_OUT_T is set).  ufair_stats_reset() initialises the private buffers
-   * once; they may keep accumulating over several calls (member chunks);
-   * ufair_stats_finalize() folds them. */
+   * The integrator only writes the T rows (so out_T must be non-NULL when stats == 1, whether or
+   * not UFAIR_OUT_T is set); ufair_stats_pass_*() then reads them once at HBM speed and adds member
+   * slice c of every row into copy c of hist_private / moments_private (counts; sum, sum of
+   * squares, min, max) in a fixed order.  ufair_stats_reset() initialises the private buffers
+   * once; they may keep accumulating over several run + pass pairs (member chunks);
+   * ufair_stats_finalize() folds the copies. */
   int32_t hist_bins;
   int32_t hist_copies;
   double hist_lo, hist_hi;
@@ -202,10 +202,10 @@ int ufair_kernel_variant(const ufair_desc* d, int32_t elem_size, uint32_t* form,
 
 /* Zero (and initialise the min/max sentinels of) the private statistics buffers. */
 int ufair_stats_reset(const ufair_desc* d, void* stream);
-/* Second pass of the statistics: fold the T rows ufair_run_* just wrote (d->out_T, same
- * descriptor, same stream) into moments_private.  One call per ufair_run_* call when stats == 1. */
-int ufair_stats_moments_f64(const ufair_desc* d, void* stream);
-int ufair_stats_moments_f32(const ufair_desc* d, void* stream);
+/* The statistics pass: per-step histogram and moments of the T rows ufair_run_* just wrote
+ * (d->out_T; same descriptor, same stream).  One call per ufair_run_* call when stats == 1. */
+int ufair_stats_pass_f64(const ufair_desc* d, void* stream);
+int ufair_stats_pass_f32(const ufair_desc* d, void* stream);
 /* Fold the private copies: hist[hist_rows][hist_bins] (uint64 counts) and
  * moments[hist_rows][UFAIR_MOM_COUNT] (sum, sumsq, min, max as doubles). */
 int ufair_stats_finalize(const ufair_desc* d, uint64_t* hist, double* moments, void* stream);

@@ -15,7 +15,7 @@ for copies in (1, 4, 16, 64, 256):
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for _ in range(5):
-        plan.reset_stats(); plan.launch(); plan.moments(); plan.finalize_stats()
+        plan.reset_stats(); plan.launch(); plan.stats_pass(); plan.finalize_stats()
     e1.record(); torch.cuda.synchronize()
     print(copies, e0.elapsed_time(e1) / 5)
     del plan
