@@ -128,7 +128,8 @@ static EncodeTiledFn encode_tiled() {
 
 // emissions [n_gas][n_t][ld] -> rank-3 map, box = MW members x kTT steps x n_gas gases;
 // f_ext [n_t][ld] -> rank-2 map, box = MW x kTT.  Out-of-range parts of a box are zero-filled.
-int make_tensor_maps(const ufair_desc* d, size_t elem, int mw_members, CUtensorMap* tmE, CUtensorMap* tmF) {
+int make_tensor_maps(const ufair_desc* d, size_t elem, int mw_members, int tile_steps, CUtensorMap* tmE,
+                     CUtensorMap* tmF) {
   memset(tmE, 0, sizeof(*tmE));
   memset(tmF, 0, sizeof(*tmF));
   const bool e_member = d->e_mode == UFAIR_E_MEMBER, f_member = d->fext_mode == UFAIR_FEXT_MEMBER;
@@ -142,7 +143,7 @@ int make_tensor_maps(const ufair_desc* d, size_t elem, int mw_members, CUtensorM
   if (e_member) {
     const cuuint64_t dims[3] = {(cuuint64_t)d->ld_member, (cuuint64_t)d->n_t, (cuuint64_t)d->n_gas};
     const cuuint64_t strides[2] = {row, row * (cuuint64_t)d->n_t};
-    const cuuint32_t box[3] = {mw, (cuuint32_t)kTT, (cuuint32_t)d->n_gas};
+    const cuuint32_t box[3] = {mw, (cuuint32_t)tile_steps, (cuuint32_t)d->n_gas};
     CUresult r = enc(tmE, dt, 3, const_cast<void*>(d->emissions), dims, strides, box, ones, CU_TENSOR_MAP_INTERLEAVE_NONE,
                      CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return set_error(UFAIR_ERR_CUDA, "cuTensorMapEncodeTiled(emissions) failed: %d", (int)r);
@@ -150,7 +151,7 @@ int make_tensor_maps(const ufair_desc* d, size_t elem, int mw_members, CUtensorM
   if (f_member) {
     const cuuint64_t dims[2] = {(cuuint64_t)d->ld_member, (cuuint64_t)d->n_t};
     const cuuint64_t strides[1] = {row};
-    const cuuint32_t box[2] = {mw, (cuuint32_t)kTT};
+    const cuuint32_t box[2] = {mw, (cuuint32_t)tile_steps};
     CUresult r = enc(tmF, dt, 2, const_cast<void*>(d->f_ext), dims, strides, box, ones, CU_TENSOR_MAP_INTERLEAVE_NONE,
                      CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return set_error(UFAIR_ERR_CUDA, "cuTensorMapEncodeTiled(f_ext) failed: %d", (int)r);

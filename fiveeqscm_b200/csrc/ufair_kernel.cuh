@@ -84,6 +84,9 @@
 #ifndef UFAIR_TT
 #define UFAIR_TT 8  // time steps per shared-memory tile (8 measured ~2 % faster than 4)
 #endif
+#ifndef UFAIR_TT_FORM  // ... for the specialised-form kernels (32 members per warp: their tiles are 3.2x as
+#define UFAIR_TT_FORM 2  // wide, and shared memory, not registers, would otherwise cap their occupancy)
+#endif
 
 namespace ufair {
 
@@ -234,17 +237,31 @@ enum { T_QM0 = 0, T_QM1, T_DEC0, T_DEC1, T_COUNT };          // q_j (1 - e^{-dt/
 constexpr int extra_rows(int amode) { return amode == UFAIR_ALPHA_NEWTON ? 3 : (amode == UFAIR_ALPHA_SINH ? 1 : 0); }
 constexpr size_t round128(size_t b) { return (b + 127) / 128 * 128; }
 
+// parameter rows of one gas when only its first `np` pools exist (the absent pools' KA / K0 rows are
+// not allocated), and the compact row of logical row k (the G_* / hot / extra numbering above)
+__host__ __device__ constexpr int gas_rows(int pg, int np) { return pg - 2 * (4 - np); }
+__host__ __device__ constexpr int compact_row(int np, int k) { return k < 4 ? k : (k < 8 ? np + (k - 4) : 2 * np + (k - 8)); }
+
 // per-WARP shared memory, in bytes (every piece 128-byte aligned: tensor-map TMA destinations)
-template <typename Real, int NGAS, int AMODE, int GPL_> struct WarpSmem {
+template <typename Real, int NGAS, int AMODE, int GPL_, unsigned FORM = 0u> struct WarpSmem {
   static constexpr int GPL = GPL_;
+  static constexpr int TT = FORM != 0 ? UFAIR_TT_FORM : kTT;  // time steps per tile
   static constexpr bool HOT_SMEM = ((GPL == 1) || sizeof(Real) == 8) && !(sizeof(Real) == 8 && (UFAIR_REGCONST & 1));
   static constexpr int MW = members_per_warp(sizeof(Real), NGAS, GPL);
   static constexpr int G_HOT = G_COLD;                            // first hot row (if in smem)
   static constexpr int G_X0 = G_COLD + (HOT_SMEM ? H_COUNT : 0);  // SINH: g0; NEWTON: g1, ln g0, 1/c
   static constexpr int PG = G_X0 + extra_rows(AMODE);             // rows per gas
-  static constexpr int ROWS = GPL * PG + T_COUNT;
-  static constexpr uint32_t e_box = (uint32_t)(NGAS * kTT * MW * sizeof(Real));  // bytes one E box delivers
-  static constexpr uint32_t f_box = (uint32_t)(kTT * MW * sizeof(Real));         // bytes one f_ext box delivers
+  // first row of gas gl / of the thermal block, and the row of logical row k of gas gl
+  static __host__ __device__ constexpr int gas_base(int gl) {
+    int b = 0;
+    for (int g = 0; g < gl; ++g) b += gas_rows(PG, form_pools(FORM, g));
+    return b;
+  }
+  static __host__ __device__ constexpr int row(int gl, int k) { return gas_base(gl) + compact_row(form_pools(FORM, gl), k); }
+  static constexpr int T_BASE = gas_base(GPL);
+  static constexpr int ROWS = T_BASE + T_COUNT;
+  static constexpr uint32_t e_box = (uint32_t)(NGAS * TT * MW * sizeof(Real));  // bytes one E box delivers
+  static constexpr uint32_t f_box = (uint32_t)(TT * MW * sizeof(Real));         // bytes one f_ext box delivers
   static constexpr uint32_t e_stage = (uint32_t)round128(e_box);
   static constexpr uint32_t f_stage = (uint32_t)round128(f_box);
   static constexpr uint32_t off_e = 0;
@@ -284,8 +301,9 @@ __global__ void __launch_bounds__(kWarps * 32, min_blocks(sizeof(Real), NGAS, GP
                            const __grid_constant__ CUtensorMap tmF) {
   static_assert(FORM == 0 || GPL_ == NGAS, "a per-gas form needs all gases of a member in one lane");
   using M = Math<Real>;
-  using WS = WarpSmem<Real, NGAS, AMODE, GPL_>;
+  using WS = WarpSmem<Real, NGAS, AMODE, GPL_, FORM>;
   constexpr int GPL = WS::GPL;           // gases this lane integrates
+  constexpr int kTT = WS::TT;            // time steps per tile (shadows the general kernels' constant)
   constexpr int GROUPS = NGAS / GPL;     // lanes per member
   constexpr int MW = WS::MW;             // members per warp
   constexpr int NACT = MW * GROUPS;      // working lanes
@@ -324,10 +342,10 @@ __global__ void __launch_bounds__(kWarps * 32, min_blocks(sizeof(Real), NGAS, GP
   pin(f_addr);
   pin(par);
   pin(tb);
-#define PARG(gl, k) lds(par + (uint32_t)((gl) * WS::PG + (k)) * 32u * ES, Real())
-#define SETG(gl, k, v) sts(par + (uint32_t)((gl) * WS::PG + (k)) * 32u * ES, (Real)(v))
-#define PART(k) lds(par + (uint32_t)(GPL * WS::PG + (k)) * 32u * ES, Real())
-#define SETT(k, v) sts(par + (uint32_t)(GPL * WS::PG + (k)) * 32u * ES, (Real)(v))
+#define PARG(gl, k) lds(par + (uint32_t)WS::row(gl, k) * 32u * ES, Real())
+#define SETG(gl, k, v) sts(par + (uint32_t)WS::row(gl, k) * 32u * ES, (Real)(v))
+#define PART(k) lds(par + (uint32_t)(WS::T_BASE + (k)) * 32u * ES, Real())
+#define SETT(k, v) sts(par + (uint32_t)(WS::T_BASE + (k)) * 32u * ES, (Real)(v))
 
   const int n_tile = (n_t + kTT - 1) / kTT;
   if (lane == 0 && use_tma) {
@@ -707,7 +725,8 @@ __global__ void __launch_bounds__(kWarps * 32, min_blocks(sizeof(Real), NGAS, GP
 }
 
 // ---- launchers: one per (Real, NGAS, AMODE), defined in ufair_inst_*.cu ----------------------------
-int make_tensor_maps(const ufair_desc* d, size_t elem, int mw_members, CUtensorMap* tmE, CUtensorMap* tmF);
+int make_tensor_maps(const ufair_desc* d, size_t elem, int mw_members, int tile_steps, CUtensorMap* tmE,
+                     CUtensorMap* tmF);
 int cuda_error(cudaError_t e, const char* what);
 
 template <typename Real, int NGAS, int AMODE>
@@ -715,9 +734,9 @@ int launch_integrate(const ufair_desc* d, const KArgs<Real>& a, cudaStream_t str
 
 template <typename Real, int NGAS, int AMODE, int GPL, unsigned FORM, bool INV = false>
 int launch_variant(const ufair_desc* d, const KArgs<Real>& a, cudaStream_t stream) {
-  using WS = WarpSmem<Real, NGAS, AMODE, GPL>;
-  CUtensorMap tmE, tmF;  // box = WS::MW members x kTT steps (x NGAS gases): depends on the lane mapping
-  const int rc = make_tensor_maps(d, sizeof(Real), WS::MW, &tmE, &tmF);
+  using WS = WarpSmem<Real, NGAS, AMODE, GPL, FORM>;
+  CUtensorMap tmE, tmF;  // box = WS::MW members x WS::TT steps (x NGAS gases): depends on the variant
+  const int rc = make_tensor_maps(d, sizeof(Real), WS::MW, WS::TT, &tmE, &tmF);
   if (rc != UFAIR_OK) return rc;
   const size_t smem = (size_t)WS::bytes(a.fext_mode == UFAIR_FEXT_MEMBER) * kWarps;
   auto kern = (a.e_mode == UFAIR_E_MEMBER) ? ufair_integrate_kernel<Real, NGAS, AMODE, true, GPL, FORM, INV>
