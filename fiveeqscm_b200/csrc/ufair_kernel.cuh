@@ -21,12 +21,15 @@
 //     v5 one 3-D tensor-map TMA per warp-tile, pinned smem addresses, running pointers: 335 instr
 //        per 10-member warp-step, IPC 0.69 at 5 warps/SMSP -> 38.7 ms (41.8 with statistics)
 //     v6 = GPL_ALL: a lane integrates all gases of its member again, now with smem constants (no
-//        redundant thermal step, no shuffles, no idle lanes: 27 instr per member-step instead of
-//        33.5) -- but 168 regs leave 3 warps/SMSP and IPC drops to 0.45: 47.8 ms.  Thread-level
-//        parallelism beats instruction count here, so GPL = 1 stays the FP64 default (FP32, with
-//        half-width state, runs GPL = NGAS at 4 warps/SMSP: 26.4 -> 14.1 ms).
+//        redundant thermal step, no shuffles, no idle lanes: 22.6 instr per member-step instead of
+//        28.2).  First measured at 47.8 ms -- but that build was capped at 8 warps/SM by its 28 KB of
+//        shared memory per warp (8-step tiles x 32 members), not by its 155 registers; with 2-step
+//        tiles (11 warps/SM) it runs the dense case in 35.5 ms, a tie with GPL = 1 (35.3 ms), which
+//        stays the FP64 default.  FP32, with half-width state, runs GPL = NGAS (26.4 -> 13.3 ms), and
+//        so do the specialised per-gas forms.
 //     final round 1: cheaper rcp / sqrt / log, single-constant decay reduction, single-warp CTAs,
-//        TT = 8: 293 instr per warp-step, FP64 pipe 62 %, 36.4 ms alone / 36.9-39.4 ms sustained.
+//        TT = 8, histogram moved out of the loop into the statistics pass: 282 instr per warp-step,
+//        FP64 pipe 68 %, 33.7 ms alone / 35.3 ms sustained.
 //   The loop body is alpha_val -> step_conc -> step_forc -> step_temp, the names the reference
 //   reserves in .coveragerc:12-19; `oxfair` is ONE launch.
 //
@@ -68,6 +71,9 @@
 #endif
 #ifndef UFAIR_MINB_F32
 #define UFAIR_MINB_F32 (32 / UFAIR_WARPS)
+#endif
+#ifndef UFAIR_MINB_F64_GPLALL  // resident WARPS per SM, FP64 general kernel with all gases of a member in one lane
+#define UFAIR_MINB_F64_GPLALL 12
 #endif
 #ifndef UFAIR_MINB_F64_FORM  // resident WARPS per SM for the specialised (per-gas form) kernels
 #define UFAIR_MINB_F64_FORM 12
@@ -245,7 +251,8 @@ __host__ __device__ constexpr int compact_row(int np, int k) { return k < 4 ? k 
 // per-WARP shared memory, in bytes (every piece 128-byte aligned: tensor-map TMA destinations)
 template <typename Real, int NGAS, int AMODE, int GPL_, unsigned FORM = 0u> struct WarpSmem {
   static constexpr int GPL = GPL_;
-  static constexpr int TT = FORM != 0 ? UFAIR_TT_FORM : kTT;  // time steps per tile
+  // time steps per tile: short tiles wherever an FP64 lane carries several gases (32 members per warp)
+  static constexpr int TT = (sizeof(Real) == 8 && GPL_ > 1) ? UFAIR_TT_FORM : kTT;
   static constexpr bool HOT_SMEM = ((GPL == 1) || sizeof(Real) == 8) && !(sizeof(Real) == 8 && (UFAIR_REGCONST & 1));
   static constexpr int MW = members_per_warp(sizeof(Real), NGAS, GPL);
   static constexpr int G_HOT = G_COLD;                            // first hot row (if in smem)
@@ -281,7 +288,7 @@ template <typename Real, int NGAS, int AMODE, int GPL_, unsigned FORM = 0u> stru
 constexpr int min_blocks(int elem_size, int n_gas, int gpl, unsigned form) {
   if (form != 0) return (elem_size == 8 ? UFAIR_MINB_F64_FORM : UFAIR_MINB_F32_FORM) / UFAIR_WARPS;
   if (elem_size == 4) return gpl == n_gas ? 16 / UFAIR_WARPS : UFAIR_MINB_F32;
-  return (gpl == n_gas && n_gas > 1) ? 12 / UFAIR_WARPS : UFAIR_MINB_F64;
+  return (gpl == n_gas && n_gas > 1) ? UFAIR_MINB_F64_GPLALL / UFAIR_WARPS : UFAIR_MINB_F64;
 }
 
 // EMEM: per-member emissions (TMA-staged tile) vs scenario-shared (read-only path + register prefetch)
