@@ -258,6 +258,9 @@ def main():
     local = int(os.environ.get("LOCAL_RANK", "0"))
     assert torch.cuda.is_available(), "bench.py (our arm) needs a GPU; there is no CPU fallback"
     torch.cuda.set_device(local)
+    # one rank per GPU: keep each rank (and the pinned host buffers it is about to allocate) on its GPU's
+    # NUMA node.  Not at N = 1, where the CPU-baseline leg wants every core of the box.
+    numa = D.bind_to_gpu_numa_node(local) if world > 1 else None
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
@@ -447,7 +450,7 @@ def main():
         d2h = ((2 * N_GAS + 1) * n_t + 18) * Me * es + n_t * spec.bins * 8 + n_t * 32
         line["e2e"] = {"value": float(Me) * n_t * n_gpus * args.e2e_steps / float(el.item()),
                        "unit": "member-timesteps/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                       "members_per_gpu": Me, "steps": args.e2e_steps,
+                       "members_per_gpu": Me, "steps": args.e2e_steps, "numa_binding": numa,
                        "what": "run_ensemble(host pinned E/params -> all of C, RF, T, state + histogram back on the host), "
                                "chunked 65536 members, H2D/kernel/D2H overlapped on 3 streams; wall clock, max over ranks"}
         # secondary: the configs[3] use case proper -- host inputs in, only the ensemble statistics back

@@ -34,3 +34,47 @@ def allreduce_stats(hist, moments, group=None):
     moments[:, 3] = ext[:, 0]
     moments[:, 2] = -ext[:, 1]
     return hist, moments
+
+
+def _parse_cpulist(text: str):
+    cpus = set()
+    for part in text.strip().split(","):
+        if not part:
+            continue
+        lo, _, hi = part.partition("-")
+        cpus.update(range(int(lo), int(hi or lo) + 1))
+    return cpus
+
+
+def numa_cpus_of_gpu(pci_domain: int, pci_bus: int, pci_device: int, sysfs: str = "/sys"):
+    """(numa node, CPUs of that node) for the GPU at PCI domain:bus:device, read from sysfs;
+    (-1, empty set) when the platform does not say (single-socket hosts report node -1)."""
+    import os
+    bdf = "%04x:%02x:%02x.0" % (pci_domain, pci_bus, pci_device)
+    try:
+        node = int(open(os.path.join(sysfs, "bus/pci/devices", bdf, "numa_node")).read().strip())
+        if node < 0:
+            return -1, set()
+        return node, _parse_cpulist(open(os.path.join(sysfs, "devices/system/node/node%d/cpulist" % node)).read())
+    except (OSError, ValueError):
+        return -1, set()
+
+
+def bind_to_gpu_numa_node(device_index: int):
+    """One process per GPU on a multi-socket host: run this rank on the CPUs of the NUMA node its
+    GPU hangs off, BEFORE allocating page-locked host buffers (first touch then places them on that
+    node), so the host pipeline's H2D / D2H copies do not cross the socket interconnect.
+    Returns dict(node, cpus) describing what was done (cpus == 0: left unchanged)."""
+    import os
+
+    import torch
+    p = torch.cuda.get_device_properties(device_index)
+    node, cpus = numa_cpus_of_gpu(p.pci_domain_id, p.pci_bus_id, p.pci_device_id)
+    try:
+        allowed = os.sched_getaffinity(0) & cpus
+        if allowed:
+            os.sched_setaffinity(0, allowed)
+            return dict(node=node, cpus=len(allowed))
+    except (AttributeError, OSError):
+        pass
+    return dict(node=node, cpus=0)

@@ -222,3 +222,19 @@ def test_host_side_form_detection_matches_the_device_rule():
     assert _detect_form_host(gpd, None) == [_abi.form(4, LOG | LIN | SQRT)] * 3
     gp0 = np.array(gp[3:4]); gp0[0, _abi.GP_F2] = 0.0       # no forcing at all: the linear term stands in
     assert _detect_form_host(gp0, None) == [_abi.form(1, LIN)]
+
+
+def test_numa_lookup_reads_sysfs(tmp_path):
+    from fiveeqscm_b200 import dist as D
+    assert D._parse_cpulist("0-3,8,10-11\n") == {0, 1, 2, 3, 8, 10, 11} and D._parse_cpulist("") == set()
+    dev = tmp_path / "bus/pci/devices/0000:1b:00.0"
+    dev.mkdir(parents=True)
+    (dev / "numa_node").write_text("1\n")
+    node = tmp_path / "devices/system/node/node1"
+    node.mkdir(parents=True)
+    (node / "cpulist").write_text("32-63,96-127\n")
+    n, cpus = D.numa_cpus_of_gpu(0, 0x1b, 0, sysfs=str(tmp_path))
+    assert n == 1 and len(cpus) == 64 and 32 in cpus and 127 in cpus and 0 not in cpus
+    (dev / "numa_node").write_text("-1\n")                          # single-socket host
+    assert D.numa_cpus_of_gpu(0, 0x1b, 0, sysfs=str(tmp_path)) == (-1, set())
+    assert D.numa_cpus_of_gpu(0, 0x99, 0, sysfs=str(tmp_path)) == (-1, set())     # unknown device
