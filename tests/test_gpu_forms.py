@@ -150,3 +150,21 @@ def test_reference_todo_cases_one_pool_gas(api):
     pulse = np.where(t >= 6, 10.0 * c * alpha * tau * (1.0 - k) * k ** (t - 6.0), 0.0)
     C = to_np(r.C)[0]
     assert np.allclose(C[:, 0], const, rtol=1e-12, atol=0) and np.allclose(C[:, 1], pulse, rtol=1e-12, atol=1e-300)
+
+
+@pytest.mark.parametrize("gases,M,n_t", [(GASES4[:3], 1001, 97), (GASES4, 33, 1), (GASES4[:2], 2, 7), (("ch4",), 129, 3)],
+                         ids=lambda v: "+".join(v) if isinstance(v, tuple) else str(v))
+def test_specialised_ragged_tiles_and_per_member_forcing(api, gases, M, n_t):
+    """Odd step counts (a ragged last 2-step tile), ragged member counts (a partial last warp) and the
+    2-D tensor-map path of per-member external forcing, all on the specialised kernels."""
+    ens = ensemble(M, n_t=n_t, dense=False, gases=gases, seed=M + n_t)
+    fx = ens["f_ext"][:, None] * (1 + 0.01 * np.arange(M))[None, :]
+    p = _plan(api, ens, f_ext=to_dev(fx), fext_per_member=True, outputs=("C", "RF", "T", "alpha"))
+    assert any(p.kernel_variant()[0]) and p.kernel_variant()[2] == 32
+    r = p.run(); _sync()
+    ref = co.oxfair(ens["E"], ens["gas_params"], ens["thermal_params"], f_ext=fx, fext_per_member=True, want_alpha=True)
+    for k in ("C", "RF", "T", "alpha", "state"):
+        assert field_relerr(to_np(getattr(r, k)), ref[k], 1e-2 if k in ("RF", "T") else 0.0) < TOL64, k
+    g = _plan(api, ens, f_ext=to_dev(fx), fext_per_member=True, outputs=("C", "RF", "T", "alpha"), gas_form=None).run(); _sync()
+    for k in ("C", "RF", "T", "alpha", "state"):
+        assert np.array_equal(to_np(getattr(r, k)), to_np(getattr(g, k))), k
