@@ -440,3 +440,32 @@ def test_host_pipeline_fp32_and_output_reuse(api):
     assert r2.T.ctypes.data == t_ptr            # same buffer, refilled
     np.testing.assert_array_equal(r2.T, to_np(dev.T))
     ws.close()
+
+
+def test_step_is_cuda_graph_capturable(api):
+    """reset + integrate + statistics pass + finalize are plain stream work (no allocation, no
+    synchronisation, tensor maps passed by value): a whole step can be captured once and replayed."""
+    import torch
+    ens = ensemble(4000, n_t=64, dense=True, seed=6)
+    spec = api.HistSpec(lo=-1.0, hi=3.0, bins=128)
+    plan = api.DevicePlan(to_dev(ens["E"]), to_dev(ens["gas_params"]), to_dev(ens["thermal_params"]), stats=spec)
+    eager = plan.run()
+    torch.cuda.synchronize()
+    want = {k: getattr(eager, k).clone() for k in ("C", "RF", "T", "hist", "moments", "state")}
+    for k in want:
+        getattr(eager, k).zero_()
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        plan.run()                                  # warm-up on the capture stream
+    torch.cuda.current_stream().wait_stream(side)
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(graph):
+        plan.run()
+    for _ in range(2):
+        for k in want:
+            getattr(plan.result, k).zero_()
+        graph.replay()
+        torch.cuda.synchronize()
+        for k, v in want.items():
+            assert torch.equal(getattr(plan.result, k), v), k
