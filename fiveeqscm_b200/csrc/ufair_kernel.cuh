@@ -44,7 +44,7 @@
 //     aligned 256-byte run per warp and row -- nothing is re-read.
 //   * optional statistics: the per-step histogram and the moments both come from a second,
 //     HBM-speed pass over the T rows this kernel writes (stats_pass_kernel, ufair_abi.cu): block-level
-//     shared-memory histograms with warp-aggregated atomics.  Measured: the in-loop version (one
+//     shared-memory histograms behind per-thread run-length merging.  Measured: the in-loop version (one
 //     RED.ADD.U32 per member-step + the binning arithmetic in every lane) cost 2 ms of the 38 ms launch,
 //     the extra work in the pass costs 0.3 ms.
 #pragma once
@@ -55,8 +55,9 @@
 #include "../../include/ufair.h"
 #include "ufair_math.cuh"
 
-// 1: a lane integrates all gases of its member; 0: one gas per lane.  Measured: FP64 is faster with
-// one gas per lane (5 warps/SMSP beat the lower instruction count); in FP32 state is half as wide.
+// 1: a lane integrates all gases of its member; 0: one gas per lane.  Measured: in FP64 the two tie on
+// dense parameters (35.3 vs 35.5 ms; see the v6 note above), one gas per lane is the default; in
+// FP32, where state is half as wide, all gases per lane wins.
 #ifndef UFAIR_GPL_ALL_F64
 #define UFAIR_GPL_ALL_F64 0
 #endif
