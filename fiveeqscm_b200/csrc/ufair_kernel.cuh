@@ -302,12 +302,17 @@ template <typename Real> __device__ __forceinline__ Real sum_pools(const Real (&
 }
 
 // GPL: gases per lane (1 or NGAS); FORM: per-gas specialisation (0 = dense; needs GPL == NGAS);
-// INV: concentration-driven gases (diagnose the emissions) and the emissions output
-template <typename Real, int NGAS, int AMODE, bool EMEM, int GPL_, unsigned FORM, bool INV>
+// VAR: kVarGeneral | kVarInverse (concentration-driven gases: diagnose the emissions, emissions
+// output) | kVarPlain (no external forcing, no iIRF ceiling, outputs exactly C + RF + T: the run-time
+// switches for those cost ~38 of the general loop's 282 instructions, issued every step even when
+// predicated off -- measured 35.6 -> 34.1 ms)
+enum { kVarGeneral = 0, kVarInverse = 1, kVarPlain = 2 };
+template <typename Real, int NGAS, int AMODE, bool EMEM, int GPL_, unsigned FORM, int VAR>
 __global__ void __launch_bounds__(kWarps * 32, min_blocks(sizeof(Real), NGAS, GPL_, FORM))
     ufair_integrate_kernel(const __grid_constant__ KArgs<Real> a, const __grid_constant__ CUtensorMap tmE,
                            const __grid_constant__ CUtensorMap tmF) {
   static_assert(FORM == 0 || GPL_ == NGAS, "a per-gas form needs all gases of a member in one lane");
+  constexpr bool INV = (VAR == kVarInverse), PLAIN = (VAR == kVarPlain);
   using M = Math<Real>;
   using WS = WarpSmem<Real, NGAS, AMODE, GPL_, FORM>;
   constexpr int GPL = WS::GPL;           // gases this lane integrates
@@ -334,8 +339,8 @@ __global__ void __launch_bounds__(kWarps * 32, min_blocks(sizeof(Real), NGAS, GP
   const long long ld = a.ld;
   const int n_t = a.n_t;
 
-  const bool fx_member = (a.fext_mode == UFAIR_FEXT_MEMBER);
-  const bool fx_scen = (a.fext_mode == UFAIR_FEXT_SCENARIO);
+  const bool fx_member = !PLAIN && (a.fext_mode == UFAIR_FEXT_MEMBER);
+  const bool fx_scen = !PLAIN && (a.fext_mode == UFAIR_FEXT_SCENARIO);
   const bool fx_any = fx_member || fx_scen;
   const bool use_tma = EMEM || fx_member;
 
@@ -434,8 +439,9 @@ __global__ void __launch_bounds__(kWarps * 32, min_blocks(sizeof(Real), NGAS, GP
     }
     // a zero forcing coefficient means a zero term; the log / sqrt is skipped only when no lane of
     // the warp needs it (voted once, outside the loop; with all gases in one lane this is per gas)
-    need_log[gl] = (TERMS & UFAIR_TERM_LOG) && __any_sync(FULL, f1v != Real(0));
-    need_sqrt[gl] = (TERMS & UFAIR_TERM_SQRT) && __any_sync(FULL, f3v != Real(0));
+    // (PLAIN: no vote, no branch in the loop -- the masks below still zero an absent term)
+    need_log[gl] = (TERMS & UFAIR_TERM_LOG) && (PLAIN || __any_sync(FULL, f1v != Real(0)));
+    need_sqrt[gl] = (TERMS & UFAIR_TERM_SQRT) && (PLAIN || __any_sync(FULL, f3v != Real(0)));
     mk1[gl] = (f1v != Real(0)) ? 0xffffffffu : 0u;
     mk3[gl] = (f3v != Real(0)) ? 0xffffffffu : 0u;
     pin(mk1[gl]);
@@ -485,12 +491,13 @@ __global__ void __launch_bounds__(kWarps * 32, min_blocks(sizeof(Real), NGAS, GP
   // bit-identical to the select it replaces because scaling by 1/2 is exact
   const Real wOld = (a.t_mode == UFAIR_T_MID) ? Real(0.5) : Real(0);
   const Real wNew = (a.t_mode == UFAIR_T_MID) ? Real(0.5) : Real(1);
-  const bool clamp = a.clamp != 0;
+  const bool clamp = !PLAIN && a.clamp != 0;
 
   // output predicates packed in one register; running output pointers (gas g0; + gl * gstride)
   const bool owner = active && (g0 == 0);  // the lane that owns the member's T / histogram count
-  unsigned wm = (active ? (unsigned)(a.out_mask & (UFAIR_OUT_C | UFAIR_OUT_RF | UFAIR_OUT_ALPHA | (INV ? UFAIR_OUT_E : 0))) : 0u) |
-                ((owner && ((a.out_mask & UFAIR_OUT_T) || a.stats)) ? (unsigned)UFAIR_OUT_T : 0u);
+  unsigned wm = PLAIN ? ((active ? (unsigned)(UFAIR_OUT_C | UFAIR_OUT_RF) : 0u) | (owner ? (unsigned)UFAIR_OUT_T : 0u))
+                      : ((active ? (unsigned)(a.out_mask & (UFAIR_OUT_C | UFAIR_OUT_RF | UFAIR_OUT_ALPHA | (INV ? UFAIR_OUT_E : 0))) : 0u) |
+                         ((owner && ((a.out_mask & UFAIR_OUT_T) || a.stats)) ? (unsigned)UFAIR_OUT_T : 0u));
   pin(wm);
   const long long gstride = (long long)n_t * ld;
   const long long o_gas = (long long)g0 * gstride + m_raw;
@@ -740,15 +747,15 @@ int cuda_error(cudaError_t e, const char* what);
 template <typename Real, int NGAS, int AMODE>
 int launch_integrate(const ufair_desc* d, const KArgs<Real>& a, cudaStream_t stream);
 
-template <typename Real, int NGAS, int AMODE, int GPL, unsigned FORM, bool INV = false>
+template <typename Real, int NGAS, int AMODE, int GPL, unsigned FORM, int VAR = kVarGeneral>
 int launch_variant(const ufair_desc* d, const KArgs<Real>& a, cudaStream_t stream) {
   using WS = WarpSmem<Real, NGAS, AMODE, GPL, FORM>;
   CUtensorMap tmE, tmF;  // box = WS::MW members x WS::TT steps (x NGAS gases): depends on the variant
   const int rc = make_tensor_maps(d, sizeof(Real), WS::MW, WS::TT, &tmE, &tmF);
   if (rc != UFAIR_OK) return rc;
   const size_t smem = (size_t)WS::bytes(a.fext_mode == UFAIR_FEXT_MEMBER) * kWarps;
-  auto kern = (a.e_mode == UFAIR_E_MEMBER) ? ufair_integrate_kernel<Real, NGAS, AMODE, true, GPL, FORM, INV>
-                                            : ufair_integrate_kernel<Real, NGAS, AMODE, false, GPL, FORM, INV>;
+  auto kern = (a.e_mode == UFAIR_E_MEMBER) ? ufair_integrate_kernel<Real, NGAS, AMODE, true, GPL, FORM, VAR>
+                                            : ufair_integrate_kernel<Real, NGAS, AMODE, false, GPL, FORM, VAR>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return cuda_error(e, "cudaFuncSetAttribute(ufair_integrate_kernel)");
   const long long n_warp = (a.n_member + WS::MW - 1) / WS::MW;
@@ -768,6 +775,12 @@ inline unsigned requested_form(const ufair_desc* d) {
 // the instantiated form the dispatcher uses for this descriptor (0 = the dense kernel)
 // concentration-driven gases / the emissions output run on the INV instantiation of the general kernel
 inline bool wants_inverse(const ufair_desc* d) { return d->conc_driven != 0 || (d->out_mask & UFAIR_OUT_E) != 0; }
+// the plain configuration: nothing optional switched on, outputs exactly C + RF + T
+inline bool is_plain(const ufair_desc* d) {
+  const int outs = UFAIR_OUT_C | UFAIR_OUT_RF | UFAIR_OUT_T | UFAIR_OUT_ALPHA | UFAIR_OUT_E;
+  return d->fext_mode == UFAIR_FEXT_NONE && !(d->iirf_max > 0.0 && isfinite(d->iirf_max)) && d->conc_driven == 0 &&
+         (d->out_mask & outs) == (UFAIR_OUT_C | UFAIR_OUT_RF | UFAIR_OUT_T);
+}
 
 inline unsigned pick_form(const ufair_desc* d) {
   const unsigned want = requested_form(d);
@@ -780,8 +793,10 @@ inline unsigned pick_form(const ufair_desc* d) {
 }
 
 // dense launcher, and the specialised forms of the EXP alpha mode when the descriptor's gas_form allows
-#define UFAIR_TRY_FORM(Real, NGAS, F) \
-  if (form == F) return launch_variant<Real, NGAS, UFAIR_ALPHA_EXP, NGAS, F>(d, a, stream);
+#define UFAIR_TRY_FORM(Real, NGAS, F)                                                                  \
+  if (form == F)                                                                                       \
+    return is_plain(d) ? launch_variant<Real, NGAS, UFAIR_ALPHA_EXP, NGAS, F, kVarPlain>(d, a, stream) \
+                       : launch_variant<Real, NGAS, UFAIR_ALPHA_EXP, NGAS, F>(d, a, stream);
 
 #define UFAIR_DEFINE_LAUNCH_EXP(Real, NGAS, TRY_FORMS)                                                 \
   template <> int launch_integrate<Real, NGAS, UFAIR_ALPHA_EXP>(const ufair_desc* d, const KArgs<Real>& a, \
@@ -789,7 +804,9 @@ inline unsigned pick_form(const ufair_desc* d) {
     const unsigned form = pick_form(d);                                                                \
     TRY_FORMS                                                                                          \
     if (wants_inverse(d))                                                                              \
-      return launch_variant<Real, NGAS, UFAIR_ALPHA_EXP, gases_per_lane(sizeof(Real), NGAS), 0u, true>(d, a, stream); \
+      return launch_variant<Real, NGAS, UFAIR_ALPHA_EXP, gases_per_lane(sizeof(Real), NGAS), 0u, kVarInverse>(d, a, stream); \
+    if (is_plain(d))                                                                                   \
+      return launch_variant<Real, NGAS, UFAIR_ALPHA_EXP, gases_per_lane(sizeof(Real), NGAS), 0u, kVarPlain>(d, a, stream); \
     return launch_variant<Real, NGAS, UFAIR_ALPHA_EXP, gases_per_lane(sizeof(Real), NGAS), 0u>(d, a, stream); \
   }
 
@@ -797,7 +814,9 @@ inline unsigned pick_form(const ufair_desc* d) {
   template <> int launch_integrate<Real, NGAS, AMODE>(const ufair_desc* d, const KArgs<Real>& a,       \
                                                       cudaStream_t stream) {                           \
     if (wants_inverse(d))                                                                              \
-      return launch_variant<Real, NGAS, AMODE, gases_per_lane(sizeof(Real), NGAS), 0u, true>(d, a, stream); \
+      return launch_variant<Real, NGAS, AMODE, gases_per_lane(sizeof(Real), NGAS), 0u, kVarInverse>(d, a, stream); \
+    if (is_plain(d))                                                                                   \
+      return launch_variant<Real, NGAS, AMODE, gases_per_lane(sizeof(Real), NGAS), 0u, kVarPlain>(d, a, stream); \
     return launch_variant<Real, NGAS, AMODE, gases_per_lane(sizeof(Real), NGAS), 0u>(d, a, stream);    \
   }
 

@@ -469,3 +469,20 @@ def test_step_is_cuda_graph_capturable(api):
         torch.cuda.synchronize()
         for k, v in want.items():
             assert torch.equal(getattr(plan.result, k), v), k
+
+
+@pytest.mark.parametrize("dense", [True, False])
+@pytest.mark.parametrize("alpha_mode", ["exp", "sinh", "newton", "one"])
+def test_plain_variant_is_bitwise_the_general_kernel(api, dense, alpha_mode):
+    """Runs with no external forcing, no iIRF ceiling and outputs exactly C + RF + T take a kernel
+    instantiation without those run-time switches; asking for alpha as well takes the general one.
+    Same arithmetic, so the same bits (and both match the oracle)."""
+    import torch
+    ens = ensemble(1234, n_t=77, dense=dense, seed=31)
+    kw = dict(alpha_mode=alpha_mode, newton_iters=2 if alpha_mode == "newton" else 0)
+    plain = _run_dev(api, ens, outputs=("C", "RF", "T"), **kw)
+    general = _run_dev(api, ens, outputs=("C", "RF", "T", "alpha"), **kw)
+    for k in ("C", "RF", "T", "state"):
+        assert torch.equal(getattr(plain, k), getattr(general, k)), k
+    ref = co.oxfair(ens["E"], ens["gas_params"], ens["thermal_params"], **_oracle_kw(kw))
+    _check(plain, ref, keys=("C", "RF", "T", "state"))
