@@ -495,7 +495,7 @@ template <typename T> __global__ void __launch_bounds__(256) peak_fma_kernel(int
   const T b = T(0.999999), c = T(1e-7);
   for (int i = 0; i < iters; ++i) {
 #pragma unroll
-    for (int j = 0; j < 8; ++j) a[j] = a[j] * b + c;  // contracted to one FMA per line
+    for (int j = 0; j < 8; ++j) a[j] = fma(a[j], b, c);  // one FMA per line (written out: the library builds with -fmad=false)
   }
   T s = 0;
 #pragma unroll

@@ -68,7 +68,7 @@
 #define UFAIR_WARPS 1  // warps per CTA.  A CTA is only a launch / shared-memory grouping (warps never
 #endif                 // synchronise); single-warp CTAs measured ~2 % faster than 4 (finer refill)
 #ifndef UFAIR_MINB_F64  // resident CTAs per SM the register allocator must allow, one gas per lane
-#define UFAIR_MINB_F64 (20 / UFAIR_WARPS)
+#define UFAIR_MINB_F64 (16 / UFAIR_WARPS)
 #endif
 #ifndef UFAIR_MINB_F32
 #define UFAIR_MINB_F32 (32 / UFAIR_WARPS)
@@ -82,11 +82,13 @@
 #ifndef UFAIR_MINB_F32_FORM
 #define UFAIR_MINB_F32_FORM 16
 #endif
-// experiment: which per-lane constants live in REGISTERS instead of shared memory (bit 0: the five
-// alpha_val constants, bit 1: the eight pool constants, bit 2: the four thermal constants).  Fewer
-// LDS wavefronts against more registers (pair with a lower UFAIR_MINB_F64).
+// which per-lane constants of the FP64 one-gas-per-lane kernels live in REGISTERS instead of shared
+// memory (bit 0: the five alpha_val constants, bit 1: the eight pool constants, bit 2: the four
+// thermal constants): fewer LDS against more registers.  Measured on the plain kernel (ms per
+// launch, [REGCONST, resident warps/SM]): [0,20] 34.5, [2,20] 34.0, [2,18] 33.8, [6,18] 33.4,
+// [3,18] 33.0, [7,18] 33.2 (spills), [7,16] 32.6 (118 registers, 229 instructions per warp-step).
 #ifndef UFAIR_REGCONST
-#define UFAIR_REGCONST 0
+#define UFAIR_REGCONST 7
 #endif
 #ifndef UFAIR_TT
 #define UFAIR_TT 8  // time steps per shared-memory tile (8 measured ~2 % faster than 4)
@@ -254,7 +256,8 @@ template <typename Real, int NGAS, int AMODE, int GPL_, unsigned FORM = 0u> stru
   static constexpr int GPL = GPL_;
   // time steps per tile: short tiles wherever an FP64 lane carries several gases (32 members per warp)
   static constexpr int TT = (sizeof(Real) == 8 && GPL_ > 1) ? UFAIR_TT_FORM : kTT;
-  static constexpr bool HOT_SMEM = ((GPL == 1) || sizeof(Real) == 8) && !(sizeof(Real) == 8 && (UFAIR_REGCONST & 1));
+  static constexpr bool REGC = sizeof(Real) == 8 && GPL_ == 1;  // UFAIR_REGCONST applies to these kernels
+  static constexpr bool HOT_SMEM = ((GPL == 1) || sizeof(Real) == 8) && !(REGC && (UFAIR_REGCONST & 1));
   static constexpr int MW = members_per_warp(sizeof(Real), NGAS, GPL);
   static constexpr int G_HOT = G_COLD;                            // first hot row (if in smem)
   static constexpr int G_X0 = G_COLD + (HOT_SMEM ? H_COUNT : 0);  // SINH: g0; NEWTON: g1, ln g0, 1/c
@@ -469,7 +472,7 @@ __global__ void __launch_bounds__(kWarps * 32, min_blocks(sizeof(Real), NGAS, GP
   }
   Real Ssum = S0 + S1;  // carried so that the mid-step mean costs one add
   __syncwarp();
-  constexpr bool POOL_REG = sizeof(Real) == 8 && (UFAIR_REGCONST & 2), THERM_REG = sizeof(Real) == 8 && (UFAIR_REGCONST & 4);
+  constexpr bool POOL_REG = WS::REGC && (UFAIR_REGCONST & 2), THERM_REG = WS::REGC && (UFAIR_REGCONST & 4);
   Real rK0[GPL][4], rKA[GPL][4], rT[T_COUNT];  // dead unless the experiment switches ask for them
 #pragma unroll
   for (int gl = 0; gl < GPL; ++gl)
