@@ -85,6 +85,8 @@ template <typename Real> static KArgs<Real> make_args(const ufair_desc* d) {
   a.e_mode = d->e_mode;
   a.fext_mode = d->fext_mode;
   a.t_mode = d->t_mode;
+  a.w_old = d->t_mode == UFAIR_T_MID ? (Real)0.5 : (Real)0;
+  a.w_new = d->t_mode == UFAIR_T_MID ? (Real)0.5 : (Real)1;
   a.out_mask = d->out_mask;
   a.stats = d->stats;
   a.newton_iters = d->newton_iters;

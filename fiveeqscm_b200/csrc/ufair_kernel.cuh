@@ -155,6 +155,7 @@ template <typename Real> struct KArgs {
   int n_scen;
   int e_mode, fext_mode, t_mode, out_mask, stats, newton_iters, clamp;
   double dt, h, iirf_max;
+  Real w_old, w_new;  // T = w_old (S1 + S2)_old + w_new (S1 + S2)_new; operands straight from the constant bank
   const Real* E;
   const int* scen_idx;
   const Real* e_scale;
@@ -492,8 +493,7 @@ __global__ void __launch_bounds__(kWarps * 32, min_blocks(sizeof(Real), NGAS, GP
   const Real hdt = (Real)(a.h / a.dt);
   // T = wOld (S1 + S2)_old + wNew (S1 + S2)_new: (1/2, 1/2) is the mid-step mean, (0, 1) the end value;
   // bit-identical to the select it replaces because scaling by 1/2 is exact
-  const Real wOld = (a.t_mode == UFAIR_T_MID) ? Real(0.5) : Real(0);
-  const Real wNew = (a.t_mode == UFAIR_T_MID) ? Real(0.5) : Real(1);
+  const Real wOld = a.w_old, wNew = a.w_new;
   const bool clamp = !PLAIN && a.clamp != 0;
 
   // output predicates packed in one register; running output pointers (gas g0; + gl * gstride)
@@ -612,8 +612,9 @@ __global__ void __launch_bounds__(kWarps * 32, min_blocks(sizeof(Real), NGAS, GP
       Real F = (TERMS & UFAIR_TERM_LIN) ? PARG(gl, G_F2) * sumR[gl] : Real(0);
       if (need_log[gl]) F = fma(PARG(gl, G_F1), M::mask(M::log_(C * PARG(gl, G_INVC0)), mk1[gl]), F);
       if (need_sqrt[gl]) F = fma(PARG(gl, G_F3), M::mask(M::sqrt_(C) - PARG(gl, G_SQRTC0), mk3[gl]), F);
-      if (wm & UFAIR_OUT_C) st_stream(pC + gl * gstride, C);
-      if (wm & UFAIR_OUT_RF) st_stream(pRF + gl * gstride, F);
+      // (PLAIN: the two lane predicates themselves, not bits re-tested every step)
+      if (PLAIN ? active : (wm & UFAIR_OUT_C) != 0) st_stream(pC + gl * gstride, C);
+      if (PLAIN ? active : (wm & UFAIR_OUT_RF) != 0) st_stream(pRF + gl * gstride, F);
       if (wm & UFAIR_OUT_ALPHA) st_stream(pC + dA + gl * gstride, alpha);
       Fsum = (gl == 0) ? F : Fsum + F;
     }
@@ -638,7 +639,7 @@ __global__ void __launch_bounds__(kWarps * 32, min_blocks(sizeof(Real), NGAS, GP
     S1 = s1;
     Ssum = Snew;
     Tprev = T;
-    if (wm & UFAIR_OUT_T) st_stream(pT, T);
+    if (PLAIN ? owner : (wm & UFAIR_OUT_T) != 0) st_stream(pT, T);
     pT += ld;
 #ifdef UFAIR_EXP_PAD  // cost-model experiment: UFAIR_EXP_PAD extra integer (or FP64) instructions per step
     {
