@@ -28,8 +28,11 @@
 //        stays the FP64 default.  FP32, with half-width state, runs GPL = NGAS (26.4 -> 13.3 ms), and
 //        so do the specialised per-gas forms.
 //     final round 1: cheaper rcp / sqrt / log, single-constant decay reduction, single-warp CTAs,
-//        TT = 8, histogram moved out of the loop into the statistics pass: 282 instr per warp-step,
-//        FP64 pipe 68 %, 33.7 ms alone / 35.3 ms sustained.
+//        TT = 8; histogram moved out of the loop into the statistics pass (36.4 -> 33.7 ms); the plain
+//        instantiation without run-time switches (-> 32.9); the 17 hottest per-lane constants in
+//        registers at 16 warps/SM (-> 31.8 ms alone, 32-33.5 ms sustained): 221 instr per warp-step,
+//        143 of them FP64, FP64 pipe 72 %.  Every variant fits cycles ~ 2 N_FP64 + N_other per
+//        warp-step.
 //   The loop body is alpha_val -> step_conc -> step_forc -> step_temp, the names the reference
 //   reserves in .coveragerc:12-19; `oxfair` is ONE launch.
 //
