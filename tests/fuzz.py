@@ -3,6 +3,8 @@ member / step counts (ragged tiles and warps), emission layout, external-forcing
 clamp, temperature mode, resume state, concentration-driven gases, sparse or dense parameters
 (specialised or general kernel) that the dedicated tests only sample by hand.  Shared by the GPU
 test (the CUDA path) and a CPU test (the numpy oracle through the same harness)."""
+import os
+
 import numpy as np
 
 from oracle import c_oracle as co
@@ -12,7 +14,7 @@ from tests.util import ensemble, field_relerr
 TOL64 = 1e-10
 GASES = ("co2", "ch4", "n2o", "hfc")
 _AM = {"exp": o.ALPHA_EXP, "sinh": o.ALPHA_SINH, "newton": o.ALPHA_NEWTON, "one": o.ALPHA_ONE}
-N_CASES = 40
+N_CASES = int(os.environ.get("UFAIR_FUZZ_CASES", "40"))   # a one-off wider sweep: UFAIR_FUZZ_CASES=400 pytest ...
 # Forcing and temperature of a run that lasts one or two steps from pre-industrial are ~1e-6 W m-2 / K,
 # and f1 ln(C / C0) at C = C0 (1 + 1e-7) is ill-conditioned in float64 whoever evaluates it (one
 # rounding of the argument is 1e-16 / 1e-7 = 1e-9 of the result; the kernel multiplies by 1/C0 where
