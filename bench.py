@@ -369,7 +369,9 @@ def main():
             pass
         t_hbm, t_fp = bytes_per_launch / (hbm_peak * 1e9), flops_per_launch / (fpeak * 1e12)
         bound = "fp64" if args.precision == "f64" else "fp32"
-        if t_hbm > t_fp:
+        # FP32 mode evaluates its exponentials / log / sqrt / reciprocals on the MUFU pipe, so the FMA-flop
+        # convention does not describe it; its binding roofline is HBM
+        if t_hbm > t_fp or args.precision == "f32":
             roof = {"bound": "hbm", "achieved": a_hbm, "peak": hbm_peak, "unit": "GB/s", "frac": a_hbm / hbm_peak}
         else:
             roof = {"bound": bound, "achieved": a_fp, "peak": fpeak, "unit": "TFLOP/s", "frac": a_fp / fpeak}

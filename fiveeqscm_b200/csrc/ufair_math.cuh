@@ -29,6 +29,10 @@
 #ifndef UFAIR_EXP_TABLE
 #define UFAIR_EXP_TABLE 0
 #endif
+// 1: FP32 exponentials on MUFU.EX2 (0: range reduction + polynomial on the FMA pipe)
+#ifndef UFAIR_F32_MUFU
+#define UFAIR_F32_MUFU 1
+#endif
 
 namespace ufair {
 
@@ -304,6 +308,38 @@ template <> struct Math<float> {
     return fmaf(nd, -kLn2Lo, r);
   }
   static __device__ __forceinline__ void fill_table(uint32_t, int) {}
+#if UFAIR_F32_MUFU
+  static __device__ __forceinline__ float ex2(float t) {
+    float e;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(t));
+    return e;
+  }
+  // m = 1 - exp(-x), x >= 0.  x < 1/4: x (1 - x/2 + x^2/6 - ... + x^5/720) (truncation < 5e-8, no
+  // cancellation); otherwise 1 - MUFU.EX2(-x log2 e) (2 ulp of e <= 0.78: <= 5e-7 of m).  Both are
+  // evaluated and one is selected (10 instructions instead of 16 for the reduction + polynomial form);
+  // x large -> ex2 underflows to 0 and m = 1; NaN propagates through both arms.
+  static __device__ __forceinline__ float decay(float x, uint32_t = 0) {
+    float q = -1.0f / 720.0f;
+    q = fmaf(q, x, 1.0f / 120.0f);
+    q = fmaf(q, x, -1.0f / 24.0f);
+    q = fmaf(q, x, 1.0f / 6.0f);
+    q = fmaf(q, x, -0.5f);
+    q = fmaf(q, x, 1.0f);
+    const float big = 1.0f - ex2(x * -kLog2e);
+    return x < 0.25f ? x * q : big;
+  }
+  // exp(u) = 2^n ex2(f), n = rint(u log2 e) clamped to +-40, f = u log2 e - n in two FMAs (so the
+  // argument rounding does not grow with |u|): 7 instructions instead of 16
+  static __device__ __forceinline__ float exp_(float u, uint32_t = 0) {
+    const float t = fmaf(u, kLog2e, kMagic);
+    int n = __float_as_int(t) - 0x4b400000;
+    const float nd = t - kMagic;
+    float f = fmaf(u, kLog2e, -nd);
+    f = fmaf(u, 1.925963033500011e-8f, f);  // log2(e) - float(log2(e))
+    n = max(min(n, 40), -40);
+    return __int_as_float(__float_as_int(ex2(f)) + (n << 23));
+  }
+#else
   static __device__ __forceinline__ float decay(float x, uint32_t = 0) {
     float y = fmaxf(-x, -30.0f);  // FMNMX is a single ALU op in FP32
     int n;
@@ -319,6 +355,7 @@ template <> struct Math<float> {
     n = max(min(n, 40), -40);
     return __int_as_float(__float_as_int(v) + (n << 23));
   }
+#endif
   static __device__ __forceinline__ float rcp(float a) {
     float y;
     asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(a));
