@@ -66,6 +66,8 @@ def parse():
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--sparse", action="store_true", help="literature-style sparse parameters (1-pool CH4/N2O)")
     ap.add_argument("--general-kernel", action="store_true", help="experiment: never pick a specialised per-gas form")
+    ap.add_argument("--fext", action="store_true", help="experiment: add a shared external-forcing series")
+    ap.add_argument("--iirf-max", type=float, default=None, help="experiment: switch the iIRF ceiling on (general kernel)")
     ap.add_argument("--no-stats", action="store_true", help="experiment: integrate without histogram/moments")
     ap.add_argument("--outputs", default="C,RF,T", help="experiment: comma list of outputs written to HBM ('' = none)")
     return ap.parse_args()
@@ -271,8 +273,12 @@ def main():
     E, gp, tp = device_ensemble(torch, M, n_t, rank, dense=not args.sparse)
     spec = None if args.no_stats else conc.HistSpec()
     outs = tuple(o for o in args.outputs.split(",") if o)
-    plan = conc.DevicePlan(E, gp, tp, stats=spec, precision=args.precision, outputs=outs,
-                           gas_form=None if args.general_kernel else "auto")
+    fx = None
+    if args.fext:
+        yr = torch.arange(n_t, device=E.device, dtype=torch.float64)
+        fx = 0.1 * torch.sin(2.0 * 3.141592653589793 * yr / 11.0)
+    plan = conc.DevicePlan(E, gp, tp, stats=spec, precision=args.precision, outputs=outs, f_ext=fx,
+                           iirf_max=args.iirf_max, gas_form=None if args.general_kernel else "auto")
     vform, vgpl, vmw = plan.kernel_variant()
     flops_step = algorithmic_flops(plan.gas_form if not args.general_kernel else (0,) * N_GAS)
     assert args.sparse or flops_step == FLOPS_PER_STEP
@@ -392,7 +398,8 @@ def main():
     # ---- the same shard with literature-style (sparse) parameters: one-pool CH4 / N2O, one forcing term
     # per gas, on the specialised kernel the library picks for them.  Secondary figure; the headline
     # above keeps the dense parameters, where nothing can be skipped.
-    if rank == 0 and world == 1 and not args.sparse and not args.general_kernel and spec is not None:
+    if (rank == 0 and world == 1 and not args.sparse and not args.general_kernel and spec is not None
+            and not args.fext and args.iirf_max is None):
         try:
             del plan, res
             torch.cuda.empty_cache()

@@ -312,14 +312,15 @@ template <typename Real> __device__ __forceinline__ Real sum_pools(const Real (&
 // VAR: kVarGeneral | kVarInverse (concentration-driven gases: diagnose the emissions, emissions
 // output) | kVarPlain (no external forcing, no iIRF ceiling, outputs exactly C + RF + T: the run-time
 // switches for those cost ~38 of the general loop's 282 instructions, issued every step even when
-// predicated off -- measured 35.6 -> 34.1 ms)
-enum { kVarGeneral = 0, kVarInverse = 1, kVarPlain = 2 };
+// predicated off -- measured 35.6 -> 34.1 ms) | kVarPlainFx (the same with external forcing, shared
+// or per member: the usual production configuration; default alpha mode only)
+enum { kVarGeneral = 0, kVarInverse = 1, kVarPlain = 2, kVarPlainFx = 3 };
 template <typename Real, int NGAS, int AMODE, bool EMEM, int GPL_, unsigned FORM, int VAR>
 __global__ void __launch_bounds__(kWarps * 32, min_blocks(sizeof(Real), NGAS, GPL_, FORM))
     ufair_integrate_kernel(const __grid_constant__ KArgs<Real> a, const __grid_constant__ CUtensorMap tmE,
                            const __grid_constant__ CUtensorMap tmF) {
   static_assert(FORM == 0 || GPL_ == NGAS, "a per-gas form needs all gases of a member in one lane");
-  constexpr bool INV = (VAR == kVarInverse), PLAIN = (VAR == kVarPlain);
+  constexpr bool INV = (VAR == kVarInverse), PLAIN = (VAR == kVarPlain || VAR == kVarPlainFx), NOFX = (VAR == kVarPlain);
   using M = Math<Real>;
   using WS = WarpSmem<Real, NGAS, AMODE, GPL_, FORM>;
   constexpr int GPL = WS::GPL;           // gases this lane integrates
@@ -346,8 +347,8 @@ __global__ void __launch_bounds__(kWarps * 32, min_blocks(sizeof(Real), NGAS, GP
   const long long ld = a.ld;
   const int n_t = a.n_t;
 
-  const bool fx_member = !PLAIN && (a.fext_mode == UFAIR_FEXT_MEMBER);
-  const bool fx_scen = !PLAIN && (a.fext_mode == UFAIR_FEXT_SCENARIO);
+  const bool fx_member = !NOFX && (a.fext_mode == UFAIR_FEXT_MEMBER);
+  const bool fx_scen = !NOFX && (a.fext_mode == UFAIR_FEXT_SCENARIO);
   const bool fx_any = fx_member || fx_scen;
   const bool use_tma = EMEM || fx_member;
 
@@ -782,11 +783,15 @@ inline unsigned requested_form(const ufair_desc* d) {
 // the instantiated form the dispatcher uses for this descriptor (0 = the dense kernel)
 // concentration-driven gases / the emissions output run on the INV instantiation of the general kernel
 inline bool wants_inverse(const ufair_desc* d) { return d->conc_driven != 0 || (d->out_mask & UFAIR_OUT_E) != 0; }
-// the plain configuration: nothing optional switched on, outputs exactly C + RF + T
-inline bool is_plain(const ufair_desc* d) {
+// the plain configurations: no iIRF ceiling, outputs exactly C + RF + T, emission-driven; without
+// external forcing (kVarPlain, every alpha mode) or with it (kVarPlainFx, default alpha mode)
+inline int plain_variant(const ufair_desc* d) {
   const int outs = UFAIR_OUT_C | UFAIR_OUT_RF | UFAIR_OUT_T | UFAIR_OUT_ALPHA | UFAIR_OUT_E;
-  return d->fext_mode == UFAIR_FEXT_NONE && !(d->iirf_max > 0.0 && isfinite(d->iirf_max)) && d->conc_driven == 0 &&
-         (d->out_mask & outs) == (UFAIR_OUT_C | UFAIR_OUT_RF | UFAIR_OUT_T);
+  if ((d->iirf_max > 0.0 && isfinite(d->iirf_max)) || d->conc_driven != 0 ||
+      (d->out_mask & outs) != (UFAIR_OUT_C | UFAIR_OUT_RF | UFAIR_OUT_T))
+    return kVarGeneral;
+  if (d->fext_mode == UFAIR_FEXT_NONE) return kVarPlain;
+  return d->alpha_mode == UFAIR_ALPHA_EXP ? kVarPlainFx : kVarGeneral;
 }
 
 inline unsigned pick_form(const ufair_desc* d) {
@@ -801,19 +806,24 @@ inline unsigned pick_form(const ufair_desc* d) {
 
 // dense launcher, and the specialised forms of the EXP alpha mode when the descriptor's gas_form allows
 #define UFAIR_TRY_FORM(Real, NGAS, F)                                                                  \
-  if (form == F)                                                                                       \
-    return is_plain(d) ? launch_variant<Real, NGAS, UFAIR_ALPHA_EXP, NGAS, F, kVarPlain>(d, a, stream) \
-                       : launch_variant<Real, NGAS, UFAIR_ALPHA_EXP, NGAS, F>(d, a, stream);
+  if (form == F) {                                                                                     \
+    if (var == kVarPlain) return launch_variant<Real, NGAS, UFAIR_ALPHA_EXP, NGAS, F, kVarPlain>(d, a, stream); \
+    if (var == kVarPlainFx) return launch_variant<Real, NGAS, UFAIR_ALPHA_EXP, NGAS, F, kVarPlainFx>(d, a, stream); \
+    return launch_variant<Real, NGAS, UFAIR_ALPHA_EXP, NGAS, F>(d, a, stream);                         \
+  }
 
 #define UFAIR_DEFINE_LAUNCH_EXP(Real, NGAS, TRY_FORMS)                                                 \
   template <> int launch_integrate<Real, NGAS, UFAIR_ALPHA_EXP>(const ufair_desc* d, const KArgs<Real>& a, \
                                                                 cudaStream_t stream) {                 \
     const unsigned form = pick_form(d);                                                                \
+    const int var = plain_variant(d);                                                                  \
     TRY_FORMS                                                                                          \
     if (wants_inverse(d))                                                                              \
       return launch_variant<Real, NGAS, UFAIR_ALPHA_EXP, gases_per_lane(sizeof(Real), NGAS), 0u, kVarInverse>(d, a, stream); \
-    if (is_plain(d))                                                                                   \
+    if (var == kVarPlain)                                                                              \
       return launch_variant<Real, NGAS, UFAIR_ALPHA_EXP, gases_per_lane(sizeof(Real), NGAS), 0u, kVarPlain>(d, a, stream); \
+    if (var == kVarPlainFx)                                                                            \
+      return launch_variant<Real, NGAS, UFAIR_ALPHA_EXP, gases_per_lane(sizeof(Real), NGAS), 0u, kVarPlainFx>(d, a, stream); \
     return launch_variant<Real, NGAS, UFAIR_ALPHA_EXP, gases_per_lane(sizeof(Real), NGAS), 0u>(d, a, stream); \
   }
 
@@ -822,7 +832,7 @@ inline unsigned pick_form(const ufair_desc* d) {
                                                       cudaStream_t stream) {                           \
     if (wants_inverse(d))                                                                              \
       return launch_variant<Real, NGAS, AMODE, gases_per_lane(sizeof(Real), NGAS), 0u, kVarInverse>(d, a, stream); \
-    if (is_plain(d))                                                                                   \
+    if (plain_variant(d) == kVarPlain)                                                                 \
       return launch_variant<Real, NGAS, AMODE, gases_per_lane(sizeof(Real), NGAS), 0u, kVarPlain>(d, a, stream); \
     return launch_variant<Real, NGAS, AMODE, gases_per_lane(sizeof(Real), NGAS), 0u>(d, a, stream);    \
   }

@@ -486,3 +486,30 @@ def test_plain_variant_is_bitwise_the_general_kernel(api, dense, alpha_mode):
         assert torch.equal(getattr(plain, k), getattr(general, k)), k
     ref = co.oxfair(ens["E"], ens["gas_params"], ens["thermal_params"], **_oracle_kw(kw))
     _check(plain, ref, keys=("C", "RF", "T", "state"))
+
+
+@pytest.mark.parametrize("dense", [True, False])
+@pytest.mark.parametrize("fext", ["shared", "scenario", "member"])
+def test_plain_variant_with_external_forcing_is_bitwise_the_general_kernel(api, dense, fext):
+    """The production configuration -- external forcing present, everything else plain -- has its own
+    instantiation (default alpha mode); asking for alpha as well takes the general kernel."""
+    import torch
+    M, n_t = 999, 61
+    ens = ensemble(M, n_t=n_t, dense=dense, seed=17)
+    S = ens["scen"].shape[2]
+    if fext == "member":
+        fx = ens["f_ext"][:, None] * (1 + 0.01 * np.arange(M))[None, :]
+        E, kw, okw = ens["E"], dict(f_ext=to_dev(fx), fext_per_member=True), dict(f_ext=fx, fext_per_member=True)
+    elif fext == "scenario":
+        fx = np.stack([ens["f_ext"] * (1 + 0.2 * s) for s in range(S)], axis=1)
+        E = ens["scen"]
+        kw = dict(f_ext=to_dev(fx), scen_idx=to_dev(ens["scen_idx"]), e_scale=to_dev(ens["e_scale"]))
+        okw = dict(f_ext=fx, scen_idx=ens["scen_idx"], e_scale=ens["e_scale"])
+    else:
+        E, kw, okw = ens["E"], dict(f_ext=to_dev(ens["f_ext"])), dict(f_ext=ens["f_ext"])
+    plain = _run_dev(api, ens, E=E, outputs=("C", "RF", "T"), **kw)
+    general = _run_dev(api, ens, E=E, outputs=("C", "RF", "T", "alpha"), **kw)
+    for k in ("C", "RF", "T", "state"):
+        assert torch.equal(getattr(plain, k), getattr(general, k)), k
+    ref = co.oxfair(E, ens["gas_params"], ens["thermal_params"], **okw)
+    _check(plain, ref, keys=("C", "RF", "T", "state"))
