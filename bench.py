@@ -61,6 +61,7 @@ def parse():
     ap.add_argument("--precision", default="f64", choices=["f64", "f32"])
     ap.add_argument("--e2e-members", type=int, default=262_144)
     ap.add_argument("--e2e-steps", type=int, default=2)
+    ap.add_argument("--e2e-chunk", type=int, default=16384, help="members per chunk of the host pipeline")
     ap.add_argument("--cpu-seconds", type=float, default=15.0, help="target CPU work for the cpu_baseline sample")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
@@ -439,7 +440,7 @@ def main():
         Eh, gph, tph = pin(E[:, :, :Me]), pin(gp[:, :, :Me]), pin(tp[:, :Me])
         outs = ("C", "RF", "T")
         out = conc.pinned_result(N_GAS, n_t, Me, outputs=outs, stats=spec, precision=args.precision)
-        ws = conc.Workspace(local, 65536)
+        ws = conc.Workspace(local, args.e2e_chunk)
         call = lambda: conc.run_ensemble(Eh, gph, tph, stats=spec, outputs=outs, precision=args.precision,
                                          workspace=ws, out=out)
         call()  # warm-up: staging allocation
@@ -461,7 +462,7 @@ def main():
                        "unit": "member-timesteps/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                        "members_per_gpu": Me, "steps": args.e2e_steps, "numa_binding": numa,
                        "what": "run_ensemble(host pinned E/params -> all of C, RF, T, state + histogram back on the host), "
-                               "chunked 65536 members, H2D/kernel/D2H overlapped on 3 streams; wall clock, max over ranks"}
+                               "chunked %d members, H2D/kernel/D2H overlapped on 3 streams; wall clock, max over ranks" % args.e2e_chunk}
         # secondary: the configs[3] use case proper -- host inputs in, only the ensemble statistics back
         # (histogram + moments; no trajectory leaves the GPU), same chunked pipeline
         if spec is not None:

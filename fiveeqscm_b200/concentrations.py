@@ -211,7 +211,7 @@ def _form_byte(f) -> int:
 def run_ensemble(emissions, gas_params, thermal_params, *, dt=1.0, scen_idx=None, e_scale=None, f_ext=None,
                  fext_per_member=False, state_in=None, alpha_mode="exp", newton_iters=0, iirf_max=None,
                  iirf_h=100.0, t_mode="mid", outputs: Sequence[str] = ("C", "RF", "T"), stats: Optional[HistSpec] = None,
-                 precision="f64", return_state=True, chunk_members=65536, workspace=None, out=None,
+                 precision="f64", return_state=True, chunk_members=16384, workspace=None, out=None,
                  gas_form="auto", conc_driven=None) -> EnsembleResult:
     """Integrate the 5-equation model for an ensemble (oxfair, .coveragerc:19, as one kernel launch).
 
@@ -442,7 +442,7 @@ def _run_device(torch, E, gp, tp, dt, scen_idx, e_scale, f_ext, fext_per_member,
 class Workspace:
     """Device staging buffers + streams of the host pipeline (reuse across calls to avoid re-allocation)."""
 
-    def __init__(self, device: int = 0, chunk_members: int = 65536):
+    def __init__(self, device: int = 0, chunk_members: int = 16384):
         self._h = C.c_void_p()
         _abi.check(_abi.lib().ufair_workspace_create(int(device), int(chunk_members), C.byref(self._h)))
 
