@@ -189,7 +189,7 @@ __global__ void __launch_bounds__(kStatsThreads)
                       Real lo, Real invw, int smem_hist, unsigned int* __restrict__ hp, double* mp) {
   using M = Math<Real>;
   extern __shared__ unsigned int sh[];
-  const int c = blockIdx.x, copies = gridDim.x, t = blockIdx.y;
+  const int c = blockIdx.y, copies = gridDim.y, t = blockIdx.x;  // t on x: no 65535 limit on the step count
   const long long m_lo = n_member * c / copies, m_hi = n_member * (c + 1) / copies;
   const Real* row = T + (long long)t * ld;
   unsigned int* grow = hp + ((size_t)c * rows + t0_row + t) * bins;
@@ -343,7 +343,8 @@ template <typename Real> int run_stats_pass(const ufair_desc* d, cudaStream_t st
   if (e != cudaSuccess) return cuda_error(e, "cudaFuncSetAttribute(stats_pass_kernel)");
   const Real lo = (Real)d->hist_lo;
   const Real invw = (Real)((Real)d->hist_bins / ((Real)d->hist_hi - (Real)d->hist_lo));
-  stats_pass_kernel<Real><<<dim3((unsigned)d->hist_copies, (unsigned)d->n_t), kStatsThreads, smem, stream>>>(
+  if (d->hist_copies > 65535) return set_error(UFAIR_ERR_ARG, "hist_copies %d > 65535", d->hist_copies);
+  stats_pass_kernel<Real><<<dim3((unsigned)d->n_t, (unsigned)d->hist_copies), kStatsThreads, smem, stream>>>(
       (const Real*)d->out_T, d->ld_member, d->n_member, d->hist_t0, d->hist_rows, d->hist_bins, lo, invw, smem_hist,
       d->hist_private, d->moments_private);
   e = cudaGetLastError();

@@ -513,3 +513,19 @@ def test_plain_variant_with_external_forcing_is_bitwise_the_general_kernel(api, 
         assert torch.equal(getattr(plain, k), getattr(general, k)), k
     ref = co.oxfair(E, ens["gas_params"], ens["thermal_params"], **okw)
     _check(plain, ref, keys=("C", "RF", "T", "state"))
+
+
+def test_more_than_65535_steps_with_statistics(api):
+    """A long sub-annual run: 70 000 steps of dt = 0.01 yr (the step count exceeds a CUDA grid's y / z limit,
+    which the statistics pass must not depend on)."""
+    import torch
+    M, n_t, dt = 64, 70_000, 0.01
+    ens = ensemble(M, n_t=n_t, dt=dt, dense=True, gases=("co2",), seed=3)
+    spec = api.HistSpec(lo=-1.0, hi=9.0, bins=200, copies=4)
+    res = api.run_ensemble(to_dev(ens["E"]), to_dev(ens["gas_params"]), to_dev(ens["thermal_params"]), dt=dt, stats=spec)
+    torch.cuda.synchronize()
+    ref = co.oxfair(ens["E"], ens["gas_params"], ens["thermal_params"], dt=dt)
+    _check(res, ref, keys=("C", "RF", "T", "state"))
+    hist, mom = co.temperature_stats(to_np(res.T), spec.lo, spec.hi, spec.bins)
+    assert np.array_equal(to_np(res.hist), hist.astype(np.int64))
+    assert np.allclose(to_np(res.moments), mom, rtol=1e-12, atol=1e-12)
