@@ -73,12 +73,24 @@ template <typename Real>
 static int run_chunks(ufair_workspace* ws, const ufair_desc* h, const ufair_desc& d) {
   const size_t es = sizeof(Real);
   const int G = h->n_gas, n_t = h->n_t;
-  const int64_t M = h->n_member, ldh = h->ld_member, chunk = ws->chunk;
-  const size_t hp = (size_t)ldh * es, dp = (size_t)chunk * es;  // host / device row pitch (bytes)
+  const int64_t M = h->n_member, ldh = h->ld_member;
   const size_t srows = UFAIR_STATE_ROWS(G);
   const bool e_member = h->e_mode == UFAIR_E_MEMBER;
   const bool fx_member = h->fext_mode == UFAIR_FEXT_MEMBER;
   const bool esc_on = !e_member && h->e_scale != nullptr;
+  // the workspace's chunk size, cut down for long runs so that the two staging sets stay within
+  // kStagingBudget bytes (rows per member grow with the step count)
+  const size_t gt = (size_t)G * n_t;
+  const size_t rows_per_member =
+      (e_member ? gt : 0) + (fx_member ? (size_t)n_t : 0) + (size_t)G * UFAIR_GP_COUNT + UFAIR_TP_COUNT +
+      (h->state_in ? srows : 0) + (esc_on ? (size_t)G : 0) + ((h->out_mask & UFAIR_OUT_C) ? gt : 0) +
+      ((h->out_mask & UFAIR_OUT_RF) ? gt : 0) + (((h->out_mask & UFAIR_OUT_T) || h->stats) ? (size_t)n_t : 0) +
+      ((h->out_mask & UFAIR_OUT_ALPHA) ? gt : 0) + ((h->out_mask & UFAIR_OUT_E) ? gt : 0) + (h->state_out ? srows : 0);
+  constexpr size_t kStagingBudget = (size_t)8 << 30;  // bytes, both staging sets together
+  int64_t fit = (int64_t)(kStagingBudget / 2 / (rows_per_member * es));
+  fit = fit / 256 * 256;
+  const int64_t chunk = std::min<int64_t>(ws->chunk, std::max<int64_t>(fit, 256));
+  const size_t hp = (size_t)ldh * es, dp = (size_t)chunk * es;  // host / device row pitch (bytes)
 
   const int64_t n_chunk = (M + chunk - 1) / chunk;
   for (int64_t c = 0; c < n_chunk; ++c) {

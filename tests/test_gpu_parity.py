@@ -529,3 +529,14 @@ def test_more_than_65535_steps_with_statistics(api):
     hist, mom = co.temperature_stats(to_np(res.T), spec.lo, spec.hi, spec.bins)
     assert np.array_equal(to_np(res.hist), hist.astype(np.int64))
     assert np.allclose(to_np(res.moments), mom, rtol=1e-12, atol=1e-12)
+
+
+def test_host_pipeline_long_run_shrinks_its_chunks(api):
+    """Staging memory grows with the step count; for long runs the pipeline cuts the chunk size down
+    (8 GB budget) instead of allocating chunk x n_t rows -- same results as the device path."""
+    M, n_t, dt = 6000, 12_000, 0.05
+    ens = ensemble(M, n_t=n_t, dt=dt, dense=False, gases=("co2", "ch4"), seed=8)
+    dev = _run_dev(api, ens, dt=dt, outputs=("C", "RF", "T", "alpha"))
+    host = api.run_ensemble(ens["E"], ens["gas_params"], ens["thermal_params"], dt=dt, outputs=("C", "RF", "T", "alpha"))
+    for k in ("C", "RF", "T", "alpha", "state"):
+        np.testing.assert_array_equal(getattr(host, k), to_np(getattr(dev, k)))
