@@ -387,7 +387,8 @@ def main():
             "kernel_ms": kernel_ms, "kernel_share_of_step": kernel_ms / ms_per_step,
             "algorithmic_bytes_per_member_step": (N_GAS + 2 * N_GAS + 1) * es,
             "algorithmic_flops_per_member_step": flops_step,
-            "kernel_variant": {"form": list(vform), "gases_per_lane": vgpl, "members_per_warp": vmw},
+            "kernel_variant": {"form": list(vform), "gases_per_lane": vgpl, "members_per_warp": vmw,
+                               "loop": plan.loop_variant},
             "hbm": {"achieved": a_hbm, "peak": hbm_peak, "unit": "GB/s", "frac": a_hbm / hbm_peak, "peak_source": hbm_src},
             bound: {"achieved": a_fp, "peak": fpeak, "unit": "TFLOP/s", "frac": a_fp / fpeak,
                     "peak_burst": fpeak_burst, "frac_of_burst": a_fp / fpeak_burst,

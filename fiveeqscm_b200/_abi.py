@@ -95,6 +95,7 @@ class UfairDesc(C.Structure):
 
 
 DIST_FIXED, DIST_LOGNORMAL, DIST_NORMAL = 0, 1, 2
+LOOP_NAMES = ("general", "conc_driven", "plain", "plain_fext", "plain_subset")   # UFAIR_LOOP_*
 
 
 class UfairSampler(C.Structure):
@@ -144,7 +145,7 @@ SIGNATURES = {
     "ufair_detect_form_f64": (C.c_int, [C.POINTER(UfairDesc), _vp, C.POINTER(C.c_uint8), _vp]),
     "ufair_detect_form_f32": (C.c_int, [C.POINTER(UfairDesc), _vp, C.POINTER(C.c_uint8), _vp]),
     "ufair_kernel_variant": (C.c_int, [C.POINTER(UfairDesc), _i32, C.POINTER(C.c_uint32), C.POINTER(_i32),
-                                       C.POINTER(_i32)]),
+                                       C.POINTER(_i32), C.POINTER(_i32)]),
     "ufair_stats_reset": (C.c_int, [C.POINTER(UfairDesc), _vp]),
     "ufair_stats_pass_f64": (C.c_int, [C.POINTER(UfairDesc), _vp]),
     "ufair_stats_pass_f32": (C.c_int, [C.POINTER(UfairDesc), _vp]),

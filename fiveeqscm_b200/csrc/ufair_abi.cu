@@ -568,7 +568,8 @@ int ufair_detect_form_f32(const ufair_desc* d, int32_t* scratch, uint8_t* form, 
   return detect_form<float>(d, scratch, form, (cudaStream_t)stream);
 }
 
-int ufair_kernel_variant(const ufair_desc* d, int32_t elem_size, uint32_t* form, int32_t* gpl, int32_t* mw) {
+int ufair_kernel_variant(const ufair_desc* d, int32_t elem_size, uint32_t* form, int32_t* gpl, int32_t* mw,
+                         int32_t* loop) {
   if (elem_size != 8 && elem_size != 4) return set_error(UFAIR_ERR_ARG, "elem_size must be 8 or 4");
   const int rc = validate_desc(d, (size_t)elem_size);
   if (rc != UFAIR_OK) return rc;
@@ -577,6 +578,7 @@ int ufair_kernel_variant(const ufair_desc* d, int32_t elem_size, uint32_t* form,
   if (form) *form = f;
   if (gpl) *gpl = g;
   if (mw) *mw = members_per_warp(elem_size, d->n_gas, g);
+  if (loop) *loop = wants_inverse(d) ? (int)kVarInverse : plain_variant(d);
   return UFAIR_OK;
 }
 

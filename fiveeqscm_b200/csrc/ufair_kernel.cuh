@@ -310,17 +310,21 @@ template <typename Real> __device__ __forceinline__ Real sum_pools(const Real (&
 
 // GPL: gases per lane (1 or NGAS); FORM: per-gas specialisation (0 = dense; needs GPL == NGAS);
 // VAR: kVarGeneral | kVarInverse (concentration-driven gases: diagnose the emissions, emissions
-// output) | kVarPlain (no external forcing, no iIRF ceiling, outputs exactly C + RF + T: the run-time
+// output) | kVarPlain (no external forcing, no iIRF ceiling, outputs among C, RF, T only: the run-time
 // switches for those cost ~38 of the general loop's 282 instructions, issued every step even when
 // predicated off -- measured 35.6 -> 34.1 ms) | kVarPlainFx (the same with external forcing, shared
 // or per member: the usual production configuration; default alpha mode only)
-enum { kVarGeneral = 0, kVarInverse = 1, kVarPlain = 2, kVarPlainFx = 3 };
+// | kVarPlainSub (any subset of C, RF, T -- typically T + statistics only -- as three lane predicates
+// fixed before the loop; external forcing optional; default alpha mode only)
+enum { kVarGeneral = UFAIR_LOOP_GENERAL, kVarInverse = UFAIR_LOOP_CONC_DRIVEN, kVarPlain = UFAIR_LOOP_PLAIN,
+       kVarPlainFx = UFAIR_LOOP_PLAIN_FEXT, kVarPlainSub = UFAIR_LOOP_PLAIN_SUBSET };
 template <typename Real, int NGAS, int AMODE, bool EMEM, int GPL_, unsigned FORM, int VAR>
 __global__ void __launch_bounds__(kWarps * 32, min_blocks(sizeof(Real), NGAS, GPL_, FORM))
     ufair_integrate_kernel(const __grid_constant__ KArgs<Real> a, const __grid_constant__ CUtensorMap tmE,
                            const __grid_constant__ CUtensorMap tmF) {
   static_assert(FORM == 0 || GPL_ == NGAS, "a per-gas form needs all gases of a member in one lane");
-  constexpr bool INV = (VAR == kVarInverse), PLAIN = (VAR == kVarPlain || VAR == kVarPlainFx), NOFX = (VAR == kVarPlain);
+  constexpr bool INV = (VAR == kVarInverse), PLAIN = (VAR >= kVarPlain), NOFX = (VAR == kVarPlain),
+                 ALLOUT = (VAR == kVarPlain || VAR == kVarPlainFx);  // C, RF and T all written: no output predicates
   using M = Math<Real>;
   using WS = WarpSmem<Real, NGAS, AMODE, GPL_, FORM>;
   constexpr int GPL = WS::GPL;           // gases this lane integrates
@@ -502,9 +506,11 @@ __global__ void __launch_bounds__(kWarps * 32, min_blocks(sizeof(Real), NGAS, GP
 
   // output predicates packed in one register; running output pointers (gas g0; + gl * gstride)
   const bool owner = active && (g0 == 0);  // the lane that owns the member's T / histogram count
-  unsigned wm = PLAIN ? ((active ? (unsigned)(UFAIR_OUT_C | UFAIR_OUT_RF) : 0u) | (owner ? (unsigned)UFAIR_OUT_T : 0u))
-                      : ((active ? (unsigned)(a.out_mask & (UFAIR_OUT_C | UFAIR_OUT_RF | UFAIR_OUT_ALPHA | (INV ? UFAIR_OUT_E : 0))) : 0u) |
-                         ((owner && ((a.out_mask & UFAIR_OUT_T) || a.stats)) ? (unsigned)UFAIR_OUT_T : 0u));
+  unsigned wm = (active ? (unsigned)(a.out_mask & (UFAIR_OUT_C | UFAIR_OUT_RF | UFAIR_OUT_ALPHA | (INV ? UFAIR_OUT_E : 0))) : 0u) |
+                ((owner && ((a.out_mask & UFAIR_OUT_T) || a.stats)) ? (unsigned)UFAIR_OUT_T : 0u);
+  // the plain instantiations keep the three store decisions as lane predicates, fixed before the loop
+  const bool st_c = active && (a.out_mask & UFAIR_OUT_C) != 0, st_rf = active && (a.out_mask & UFAIR_OUT_RF) != 0,
+             st_t = owner && ((a.out_mask & UFAIR_OUT_T) != 0 || a.stats != 0);
   pin(wm);
   const long long gstride = (long long)n_t * ld;
   const long long o_gas = (long long)g0 * gstride + m_raw;
@@ -616,10 +622,10 @@ __global__ void __launch_bounds__(kWarps * 32, min_blocks(sizeof(Real), NGAS, GP
       Real F = (TERMS & UFAIR_TERM_LIN) ? PARG(gl, G_F2) * sumR[gl] : Real(0);
       if (need_log[gl]) F = fma(PARG(gl, G_F1), M::mask(M::log_(C * PARG(gl, G_INVC0)), mk1[gl]), F);
       if (need_sqrt[gl]) F = fma(PARG(gl, G_F3), M::mask(M::sqrt_(C) - PARG(gl, G_SQRTC0), mk3[gl]), F);
-      // (PLAIN: the two lane predicates themselves, not bits re-tested every step)
-      if (PLAIN ? active : (wm & UFAIR_OUT_C) != 0) st_stream(pC + gl * gstride, C);
-      if (PLAIN ? active : (wm & UFAIR_OUT_RF) != 0) st_stream(pRF + gl * gstride, F);
-      if (wm & UFAIR_OUT_ALPHA) st_stream(pC + dA + gl * gstride, alpha);
+      // (PLAIN: the lane predicates themselves, not bits re-tested every step)
+      if (ALLOUT ? active : PLAIN ? st_c : (wm & UFAIR_OUT_C) != 0) st_stream(pC + gl * gstride, C);
+      if (ALLOUT ? active : PLAIN ? st_rf : (wm & UFAIR_OUT_RF) != 0) st_stream(pRF + gl * gstride, F);
+      if (!PLAIN && (wm & UFAIR_OUT_ALPHA)) st_stream(pC + dA + gl * gstride, alpha);
       Fsum = (gl == 0) ? F : Fsum + F;
     }
     pC += ld;
@@ -643,7 +649,7 @@ __global__ void __launch_bounds__(kWarps * 32, min_blocks(sizeof(Real), NGAS, GP
     S1 = s1;
     Ssum = Snew;
     Tprev = T;
-    if (PLAIN ? owner : (wm & UFAIR_OUT_T) != 0) st_stream(pT, T);
+    if (ALLOUT ? owner : PLAIN ? st_t : (wm & UFAIR_OUT_T) != 0) st_stream(pT, T);
     pT += ld;
 #ifdef UFAIR_EXP_PAD  // cost-model experiment: UFAIR_EXP_PAD extra integer (or FP64) instructions per step
     {
@@ -783,13 +789,15 @@ inline unsigned requested_form(const ufair_desc* d) {
 // the instantiated form the dispatcher uses for this descriptor (0 = the dense kernel)
 // concentration-driven gases / the emissions output run on the INV instantiation of the general kernel
 inline bool wants_inverse(const ufair_desc* d) { return d->conc_driven != 0 || (d->out_mask & UFAIR_OUT_E) != 0; }
-// the plain configurations: no iIRF ceiling, outputs exactly C + RF + T, emission-driven; without
-// external forcing (kVarPlain, every alpha mode) or with it (kVarPlainFx, default alpha mode)
+// the plain configurations: no iIRF ceiling, outputs among C, RF, T only, emission-driven.  All three
+// outputs: without external forcing (kVarPlain, every alpha mode) or with it (kVarPlainFx, default
+// alpha mode); a subset of them: kVarPlainSub (default alpha mode)
 inline int plain_variant(const ufair_desc* d) {
-  const int outs = UFAIR_OUT_C | UFAIR_OUT_RF | UFAIR_OUT_T | UFAIR_OUT_ALPHA | UFAIR_OUT_E;
   if ((d->iirf_max > 0.0 && isfinite(d->iirf_max)) || d->conc_driven != 0 ||
-      (d->out_mask & outs) != (UFAIR_OUT_C | UFAIR_OUT_RF | UFAIR_OUT_T))
+      (d->out_mask & (UFAIR_OUT_ALPHA | UFAIR_OUT_E)) != 0)
     return kVarGeneral;
+  const int crt = UFAIR_OUT_C | UFAIR_OUT_RF | UFAIR_OUT_T;
+  if ((d->out_mask & crt) != crt) return d->alpha_mode == UFAIR_ALPHA_EXP ? kVarPlainSub : kVarGeneral;
   if (d->fext_mode == UFAIR_FEXT_NONE) return kVarPlain;
   return d->alpha_mode == UFAIR_ALPHA_EXP ? kVarPlainFx : kVarGeneral;
 }
@@ -809,6 +817,7 @@ inline unsigned pick_form(const ufair_desc* d) {
   if (form == F) {                                                                                     \
     if (var == kVarPlain) return launch_variant<Real, NGAS, UFAIR_ALPHA_EXP, NGAS, F, kVarPlain>(d, a, stream); \
     if (var == kVarPlainFx) return launch_variant<Real, NGAS, UFAIR_ALPHA_EXP, NGAS, F, kVarPlainFx>(d, a, stream); \
+    if (var == kVarPlainSub) return launch_variant<Real, NGAS, UFAIR_ALPHA_EXP, NGAS, F, kVarPlainSub>(d, a, stream); \
     return launch_variant<Real, NGAS, UFAIR_ALPHA_EXP, NGAS, F>(d, a, stream);                         \
   }
 
@@ -824,6 +833,8 @@ inline unsigned pick_form(const ufair_desc* d) {
       return launch_variant<Real, NGAS, UFAIR_ALPHA_EXP, gases_per_lane(sizeof(Real), NGAS), 0u, kVarPlain>(d, a, stream); \
     if (var == kVarPlainFx)                                                                            \
       return launch_variant<Real, NGAS, UFAIR_ALPHA_EXP, gases_per_lane(sizeof(Real), NGAS), 0u, kVarPlainFx>(d, a, stream); \
+    if (var == kVarPlainSub)                                                                           \
+      return launch_variant<Real, NGAS, UFAIR_ALPHA_EXP, gases_per_lane(sizeof(Real), NGAS), 0u, kVarPlainSub>(d, a, stream); \
     return launch_variant<Real, NGAS, UFAIR_ALPHA_EXP, gases_per_lane(sizeof(Real), NGAS), 0u>(d, a, stream); \
   }
 

@@ -196,9 +196,17 @@ int ufair_detect_form_f32(const ufair_desc* d, int32_t* scratch, uint8_t* form, 
 
 /* Which integrator variant ufair_run_* launches for this descriptor (informational / tests):
  * *form = the specialised per-gas form in use, packed one UFAIR_FORM byte per gas (0 = the general
- * kernel), *gases_per_lane and *members_per_warp = the lane mapping.  elem_size: 8 (f64) or 4 (f32). */
+ * kernel), *gases_per_lane and *members_per_warp = the lane mapping, *loop = UFAIR_LOOP_*: which
+ * instantiation of the time loop (all of them give bit-identical results; the plain ones carry no
+ * run-time switches for features that are off).  elem_size: 8 (f64) or 4 (f32).  Out-pointers may be NULL. */
+enum { UFAIR_LOOP_GENERAL = 0,      /* every run-time option                                         */
+       UFAIR_LOOP_CONC_DRIVEN = 1,  /* concentration-driven gases / emissions output                 */
+       UFAIR_LOOP_PLAIN = 2,        /* no f_ext, no iIRF ceiling, outputs exactly C + RF + T         */
+       UFAIR_LOOP_PLAIN_FEXT = 3,   /* the same with external forcing (default alpha mode)           */
+       UFAIR_LOOP_PLAIN_SUBSET = 4  /* a subset of C, RF, T (e.g. T + statistics only), with or
+                                       without external forcing (default alpha mode)                */ };
 int ufair_kernel_variant(const ufair_desc* d, int32_t elem_size, uint32_t* form, int32_t* gases_per_lane,
-                         int32_t* members_per_warp);
+                         int32_t* members_per_warp, int32_t* loop);
 
 /* Zero (and initialise the min/max sentinels of) the private statistics buffers. */
 int ufair_stats_reset(const ufair_desc* d, void* stream);

@@ -484,6 +484,10 @@ def test_plain_variant_is_bitwise_the_general_kernel(api, dense, alpha_mode):
     general = _run_dev(api, ens, outputs=("C", "RF", "T", "alpha"), **kw)
     for k in ("C", "RF", "T", "state"):
         assert torch.equal(getattr(plain, k), getattr(general, k)), k
+    t_only = _run_dev(api, ens, outputs=("T",), **kw)       # the output-subset instantiation (default alpha mode)
+    rf_only = _run_dev(api, ens, outputs=("RF",), stats=api.HistSpec(), **kw)
+    assert torch.equal(t_only.T, general.T) and t_only.C is None and torch.equal(t_only.state, general.state)
+    assert torch.equal(rf_only.RF, general.RF) and int(rf_only.hist.sum()) == 1234 * 77
     ref = co.oxfair(ens["E"], ens["gas_params"], ens["thermal_params"], **_oracle_kw(kw))
     _check(plain, ref, keys=("C", "RF", "T", "state"))
 
@@ -540,3 +544,22 @@ def test_host_pipeline_long_run_shrinks_its_chunks(api):
     host = api.run_ensemble(ens["E"], ens["gas_params"], ens["thermal_params"], dt=dt, outputs=("C", "RF", "T", "alpha"))
     for k in ("C", "RF", "T", "alpha", "state"):
         np.testing.assert_array_equal(getattr(host, k), to_np(getattr(dev, k)))
+
+
+def test_loop_variant_selection(api):
+    """Which instantiation of the time loop the dispatcher takes (include/ufair.h UFAIR_LOOP_*)."""
+    ens = ensemble(64, n_t=8, dense=True, seed=1)
+    mk = lambda **kw: api.DevicePlan(to_dev(ens["E"]), to_dev(ens["gas_params"]), to_dev(ens["thermal_params"]), **kw)
+
+    def loop(**kw):
+        p = mk(**kw)
+        p.kernel_variant()
+        return p.loop_variant
+
+    fx = to_dev(ens["f_ext"])
+    assert loop() == "plain" and loop(stats=api.HistSpec()) == "plain" and loop(alpha_mode="sinh") == "plain"
+    assert loop(f_ext=fx) == "plain_fext" and loop(f_ext=fx, alpha_mode="newton", newton_iters=1) == "general"
+    assert loop(iirf_max=97.0) == "general" and loop(outputs=("C", "RF", "T", "alpha")) == "general"
+    assert loop(outputs=("T",)) == "plain_subset" and loop(outputs=(), stats=api.HistSpec(), f_ext=fx) == "plain_subset"
+    assert loop(outputs=("T",), alpha_mode="sinh") == "general"
+    assert loop(conc_driven=True) == "conc_driven" and loop(outputs=("C", "RF", "T", "E")) == "conc_driven"
