@@ -93,6 +93,16 @@
 #ifndef UFAIR_REGCONST
 #define UFAIR_REGCONST 7
 #endif
+// the same switch for the FP32 general kernels (all gases of a member in one lane; their alpha_val
+// constants are in registers anyway), and the resident warps/SM their register budget is set for.
+// Measured (ms per launch, [REGCONST_F32, warps/SM]): [0,16] 9.7, [2,16] 9.7, [6,16] 9.5, [2,12] 9.3,
+// [6,12] 9.1 (128 registers, 295 instructions per 32-member warp-step).
+#ifndef UFAIR_REGCONST_F32
+#define UFAIR_REGCONST_F32 6
+#endif
+#ifndef UFAIR_MINB_F32_GPLALL
+#define UFAIR_MINB_F32_GPLALL 12
+#endif
 #ifndef UFAIR_TT
 #define UFAIR_TT 8  // time steps per shared-memory tile (8 measured ~2 % faster than 4)
 #endif
@@ -260,7 +270,7 @@ template <typename Real, int NGAS, int AMODE, int GPL_, unsigned FORM = 0u> stru
   static constexpr int GPL = GPL_;
   // time steps per tile: short tiles wherever an FP64 lane carries several gases (32 members per warp)
   static constexpr int TT = (sizeof(Real) == 8 && GPL_ > 1) ? UFAIR_TT_FORM : kTT;
-  static constexpr bool REGC = sizeof(Real) == 8 && GPL_ == 1;  // UFAIR_REGCONST applies to these kernels
+  static constexpr bool REGC = (sizeof(Real) == 8 && GPL_ == 1) || (sizeof(Real) == 4 && UFAIR_REGCONST_F32 != 0 && FORM == 0);
   static constexpr bool HOT_SMEM = ((GPL == 1) || sizeof(Real) == 8) && !(REGC && (UFAIR_REGCONST & 1));
   static constexpr int MW = members_per_warp(sizeof(Real), NGAS, GPL);
   static constexpr int G_HOT = G_COLD;                            // first hot row (if in smem)
@@ -295,7 +305,7 @@ template <typename Real, int NGAS, int AMODE, int GPL_, unsigned FORM = 0u> stru
 // resident CTAs per SM the register allocator must allow
 constexpr int min_blocks(int elem_size, int n_gas, int gpl, unsigned form) {
   if (form != 0) return (elem_size == 8 ? UFAIR_MINB_F64_FORM : UFAIR_MINB_F32_FORM) / UFAIR_WARPS;
-  if (elem_size == 4) return gpl == n_gas ? 16 / UFAIR_WARPS : UFAIR_MINB_F32;
+  if (elem_size == 4) return gpl == n_gas ? UFAIR_MINB_F32_GPLALL / UFAIR_WARPS : UFAIR_MINB_F32;
   return (gpl == n_gas && n_gas > 1) ? UFAIR_MINB_F64_GPLALL / UFAIR_WARPS : UFAIR_MINB_F64;
 }
 
@@ -481,7 +491,8 @@ __global__ void __launch_bounds__(kWarps * 32, min_blocks(sizeof(Real), NGAS, GP
   }
   Real Ssum = S0 + S1;  // carried so that the mid-step mean costs one add
   __syncwarp();
-  constexpr bool POOL_REG = WS::REGC && (UFAIR_REGCONST & 2), THERM_REG = WS::REGC && (UFAIR_REGCONST & 4);
+  constexpr int RCM = sizeof(Real) == 8 ? UFAIR_REGCONST : UFAIR_REGCONST_F32;
+  constexpr bool POOL_REG = WS::REGC && (RCM & 2), THERM_REG = WS::REGC && (RCM & 4);
   Real rK0[GPL][4], rKA[GPL][4], rT[T_COUNT];  // dead unless the experiment switches ask for them
 #pragma unroll
   for (int gl = 0; gl < GPL; ++gl)
