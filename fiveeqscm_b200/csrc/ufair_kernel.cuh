@@ -80,7 +80,7 @@
 #define UFAIR_MINB_F64_GPLALL 12
 #endif
 #ifndef UFAIR_MINB_F64_FORM  // resident WARPS per SM for the specialised (per-gas form) kernels
-#define UFAIR_MINB_F64_FORM 12
+#define UFAIR_MINB_F64_FORM 10
 #endif
 #ifndef UFAIR_MINB_F32_FORM
 #define UFAIR_MINB_F32_FORM 16
@@ -99,6 +99,11 @@
 // [6,12] 9.1 (128 registers, 295 instructions per 32-member warp-step).
 #ifndef UFAIR_REGCONST_F32
 #define UFAIR_REGCONST_F32 6
+#endif
+// ... and for the FP64 specialised-form kernels.  Measured (literature parameters, ms per launch,
+// [REGCONST_FORM, warps/SM]): [0,12] 19.8-20.4, [2,12] 19.6, [6,12] 19.6, [7,10] 19.0 (157 registers).
+#ifndef UFAIR_REGCONST_FORM
+#define UFAIR_REGCONST_FORM 7
 #endif
 #ifndef UFAIR_MINB_F32_GPLALL
 #define UFAIR_MINB_F32_GPLALL 12
@@ -270,8 +275,10 @@ template <typename Real, int NGAS, int AMODE, int GPL_, unsigned FORM = 0u> stru
   static constexpr int GPL = GPL_;
   // time steps per tile: short tiles wherever an FP64 lane carries several gases (32 members per warp)
   static constexpr int TT = (sizeof(Real) == 8 && GPL_ > 1) ? UFAIR_TT_FORM : kTT;
-  static constexpr bool REGC = (sizeof(Real) == 8 && GPL_ == 1) || (sizeof(Real) == 4 && UFAIR_REGCONST_F32 != 0 && FORM == 0);
-  static constexpr bool HOT_SMEM = ((GPL == 1) || sizeof(Real) == 8) && !(REGC && (UFAIR_REGCONST & 1));
+  // which constants live in registers (bit 0 alpha_val, bit 1 pools, bit 2 thermal): see UFAIR_REGCONST*
+  static constexpr int RCM = sizeof(Real) == 4 ? ((FORM == 0 && GPL_ > 1) ? UFAIR_REGCONST_F32 : 0)
+                             : (GPL_ == 1 ? UFAIR_REGCONST : (FORM != 0 ? UFAIR_REGCONST_FORM : 0));
+  static constexpr bool HOT_SMEM = ((GPL == 1) || sizeof(Real) == 8) && !(RCM & 1);
   static constexpr int MW = members_per_warp(sizeof(Real), NGAS, GPL);
   static constexpr int G_HOT = G_COLD;                            // first hot row (if in smem)
   static constexpr int G_X0 = G_COLD + (HOT_SMEM ? H_COUNT : 0);  // SINH: g0; NEWTON: g1, ln g0, 1/c
@@ -491,8 +498,7 @@ __global__ void __launch_bounds__(kWarps * 32, min_blocks(sizeof(Real), NGAS, GP
   }
   Real Ssum = S0 + S1;  // carried so that the mid-step mean costs one add
   __syncwarp();
-  constexpr int RCM = sizeof(Real) == 8 ? UFAIR_REGCONST : UFAIR_REGCONST_F32;
-  constexpr bool POOL_REG = WS::REGC && (RCM & 2), THERM_REG = WS::REGC && (RCM & 4);
+  constexpr bool POOL_REG = (WS::RCM & 2) != 0, THERM_REG = (WS::RCM & 4) != 0;
   Real rK0[GPL][4], rKA[GPL][4], rT[T_COUNT];  // dead unless the experiment switches ask for them
 #pragma unroll
   for (int gl = 0; gl < GPL; ++gl)
