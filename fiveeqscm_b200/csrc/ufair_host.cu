@@ -188,6 +188,17 @@ static int run_chunks(ufair_workspace* ws, const ufair_desc* h, const ufair_desc
   return UFAIR_OK;
 }
 
+// like CK, but first waits for the copies already queued from the caller's host buffers, so that no
+// transfer is still reading them when the error is reported
+#define CKS(call, what)                      \
+  do {                                       \
+    cudaError_t e__ = (call);                \
+    if (e__ != cudaSuccess) {                \
+      cudaStreamSynchronize(ws->s_in);       \
+      return cuda_error(e__, what);          \
+    }                                        \
+  } while (0)
+
 template <typename Real> static int run_host(ufair_workspace* ws, const ufair_desc* h, uint64_t* hist, double* moments) {
   if (!ws) return set_error(UFAIR_ERR_ARG, "workspace is NULL");
   if (!h || h->struct_size != sizeof(ufair_desc)) return set_error(UFAIR_ERR_ARG, "bad descriptor");
@@ -209,29 +220,38 @@ template <typename Real> static int run_host(ufair_workspace* ws, const ufair_de
     d.emissions = ws->e_scen.p;
   }
   if (h->fext_mode == UFAIR_FEXT_SCENARIO) {
-    if (!h->f_ext) return set_error(UFAIR_ERR_ARG, "fext_mode set but f_ext is NULL");
+    if (!h->f_ext) {
+      cudaStreamSynchronize(ws->s_in);
+      return set_error(UFAIR_ERR_ARG, "fext_mode set but f_ext is NULL");
+    }
     const size_t nb = (size_t)n_t * h->n_scen * es;
-    CK(ws->fext_scen.reserve(nb), "cudaMalloc(fext_scen)");
-    CK(cudaMemcpyAsync(ws->fext_scen.p, h->f_ext, nb, cudaMemcpyHostToDevice, ws->s_in), "H2D scenario forcing");
+    CKS(ws->fext_scen.reserve(nb), "cudaMalloc(fext_scen)");
+    CKS(cudaMemcpyAsync(ws->fext_scen.p, h->f_ext, nb, cudaMemcpyHostToDevice, ws->s_in), "H2D scenario forcing");
     d.f_ext = ws->fext_scen.p;
   }
   if (h->stats) {
-    if (h->hist_bins < 1 || !(h->hist_hi > h->hist_lo)) return set_error(UFAIR_ERR_ARG, "bad histogram spec");
+    if (h->hist_bins < 1 || !(h->hist_hi > h->hist_lo)) {
+      cudaStreamSynchronize(ws->s_in);
+      return set_error(UFAIR_ERR_ARG, "bad histogram spec");
+    }
     d.hist_copies = h->hist_copies > 0 ? h->hist_copies : 16;
     d.hist_t0 = 0;
     d.hist_rows = n_t;
     const size_t rows = (size_t)d.hist_copies * n_t;
-    CK(ws->hist_private.reserve(rows * h->hist_bins * sizeof(uint32_t)), "cudaMalloc(hist_private)");
-    CK(ws->mom_private.reserve(rows * UFAIR_MOM_COUNT * sizeof(double)), "cudaMalloc(mom_private)");
-    CK(ws->hist_out.reserve((size_t)n_t * h->hist_bins * sizeof(uint64_t)), "cudaMalloc(hist)");
-    CK(ws->mom_out.reserve((size_t)n_t * UFAIR_MOM_COUNT * sizeof(double)), "cudaMalloc(moments)");
+    CKS(ws->hist_private.reserve(rows * h->hist_bins * sizeof(uint32_t)), "cudaMalloc(hist_private)");
+    CKS(ws->mom_private.reserve(rows * UFAIR_MOM_COUNT * sizeof(double)), "cudaMalloc(mom_private)");
+    CKS(ws->hist_out.reserve((size_t)n_t * h->hist_bins * sizeof(uint64_t)), "cudaMalloc(hist)");
+    CKS(ws->mom_out.reserve((size_t)n_t * UFAIR_MOM_COUNT * sizeof(double)), "cudaMalloc(moments)");
     d.hist_private = (uint32_t*)ws->hist_private.p;
     d.moments_private = (double*)ws->mom_private.p;
     int rc = ufair_stats_reset(&d, ws->s_run);
-    if (rc != UFAIR_OK) return rc;
+    if (rc != UFAIR_OK) {
+      cudaStreamSynchronize(ws->s_in);
+      return rc;
+    }
   }
   cudaEvent_t shared_up;
-  CK(cudaEventCreateWithFlags(&shared_up, cudaEventDisableTiming), "cudaEventCreate");
+  CKS(cudaEventCreateWithFlags(&shared_up, cudaEventDisableTiming), "cudaEventCreate");
   cudaEventRecord(shared_up, ws->s_in);
   cudaStreamWaitEvent(ws->s_run, shared_up, 0);
 

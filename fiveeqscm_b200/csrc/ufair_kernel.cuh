@@ -668,58 +668,9 @@ __global__ void __launch_bounds__(kWarps * 32, min_blocks(sizeof(Real), NGAS, GP
     Tprev = T;
     if (ALLOUT ? owner : PLAIN ? st_t : (wm & UFAIR_OUT_T) != 0) st_stream(pT, T);
     pT += ld;
-#ifdef UFAIR_EXP_PAD  // cost-model experiment: UFAIR_EXP_PAD extra integer (or FP64) instructions per step
-    {
-      uint32_t pad = wm;
-#pragma unroll
-      for (int q = 0; q < UFAIR_EXP_PAD; ++q) asm volatile("add.u32 %0, %0, 1;" : "+r"(pad));
-      if (pad == 0xdeadbeefu) wm ^= 1u;
-    }
-#endif
-#ifdef UFAIR_EXP_PAD64
-    {
-      double pad = (double)Tprev;
-#pragma unroll
-      for (int q = 0; q < UFAIR_EXP_PAD64; ++q) asm volatile("add.f64 %0, %0, 0d3FF0000000000000;" : "+d"(pad));
-      if (pad == -12345.0) wm ^= 1u;
-    }
-#endif
-#ifdef UFAIR_EXP_PADUR  // same, but DFMAs whose multiplier / addend come from uniform registers (like Horner steps)
-    {
-      double pad = (double)Tprev;
-#pragma unroll
-      for (int q = 0; q < UFAIR_EXP_PADUR; ++q) pad = fma(pad, cExpQ[q % 10], cExpQ[(q + 3) % 10]);
-      if (pad == -12345.0) wm ^= 1u;
-    }
-#endif
-#ifdef UFAIR_EXP_PADUR4  // UR-operand DFMAs again, but as four INDEPENDENT chains (throughput, not latency)
-    {
-      double p0 = (double)Tprev, p1 = (double)S0, p2 = (double)S1, p3 = (double)Ssum;
-#pragma unroll
-      for (int q = 0; q < UFAIR_EXP_PADUR4 / 4; ++q) {
-        p0 = fma(p0, cExpQ[q % 10], cExpQ[(q + 3) % 10]);
-        p1 = fma(p1, cExpQ[(q + 1) % 10], cExpQ[(q + 4) % 10]);
-        p2 = fma(p2, cExpQ[(q + 2) % 10], cExpQ[(q + 5) % 10]);
-        p3 = fma(p3, cExpQ[(q + 6) % 10], cExpQ[(q + 7) % 10]);
-      }
-      if (p0 + p1 + p2 + p3 == -12345.0) wm ^= 1u;
-    }
-#endif
-#ifdef UFAIR_EXP_PADRRU  // DFMA chain with ONE uniform-register operand (the Horner form q = fma(q, r, c))
-    {
-      double pad = (double)Tprev, rr = (double)S0;
-#pragma unroll
-      for (int q = 0; q < UFAIR_EXP_PADRRU; ++q) pad = fma(pad, rr, cExpQ[q % 10]);
-      if (pad == -12345.0) wm ^= 1u;
-    }
-#endif
-#ifdef UFAIR_EXP_PADR3  // same, DFMAs with three distinct vector-register sources
-    {
-      double pad = (double)Tprev, p2 = (double)S0, p3 = (double)S1;
-#pragma unroll
-      for (int q = 0; q < UFAIR_EXP_PADR3; ++q) asm volatile("fma.rn.f64 %0, %0, %1, %2;" : "+d"(pad) : "d"(p2), "d"(p3));
-      if (pad == -12345.0) wm ^= 1u;
-    }
+#if defined(UFAIR_EXP_PAD) || defined(UFAIR_EXP_PAD64) || defined(UFAIR_EXP_PADUR) || defined(UFAIR_EXP_PADUR4) || \
+    defined(UFAIR_EXP_PADRRU) || defined(UFAIR_EXP_PADR3)
+#include "ufair_kernel_pads.inc"  // cost-model experiments; never in the shipped build
 #endif
   };
 
