@@ -65,6 +65,7 @@ def parse():
     ap.add_argument("--cpu-seconds", type=float, default=15.0, help="target CPU work for the cpu_baseline sample")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-lit", action="store_true", help="skip the secondary literature-parameter measurement")
     ap.add_argument("--sparse", action="store_true", help="literature-style sparse parameters (1-pool CH4/N2O)")
     ap.add_argument("--general-kernel", action="store_true", help="experiment: never pick a specialised per-gas form")
     ap.add_argument("--fext", action="store_true", help="experiment: add a shared external-forcing series")
@@ -401,7 +402,7 @@ def main():
     # per gas, on the specialised kernel the library picks for them.  Secondary figure; the headline
     # above keeps the dense parameters, where nothing can be skipped.
     if (rank == 0 and world == 1 and not args.sparse and not args.general_kernel and spec is not None
-            and not args.fext and args.iirf_max is None):
+            and not args.fext and args.iirf_max is None and not args.no_lit):
         try:
             del plan, res
             torch.cuda.empty_cache()

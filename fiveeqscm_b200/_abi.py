@@ -160,6 +160,7 @@ SIGNATURES = {
     "ufair_workspace_destroy": (C.c_int, [_vp]),
     "ufair_run_host_f64": (C.c_int, [_vp, C.POINTER(UfairDesc), _vp, _vp]),
     "ufair_run_host_f32": (C.c_int, [_vp, C.POINTER(UfairDesc), _vp, _vp]),
+    "ufair_link_probe": (C.c_int, [C.c_int, _i64, _i32, _i32, _i32, _pd]),
     "ufair_math_probe_f64": (C.c_int, [C.c_int, _vp, _vp, _i64, _vp]),
     "ufair_math_probe_f32": (C.c_int, [C.c_int, _vp, _vp, _i64, _vp]),
     "ufair_peak_fp64": (C.c_int, [C.c_int, _pd, _pd, _vp]),

@@ -8,6 +8,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <string.h>
+#include <time.h>
 
 #include <algorithm>
 #include <new>
@@ -336,3 +337,106 @@ int ufair_run_host_f32(ufair_workspace* ws, const ufair_desc* d, uint64_t* hist,
 }
 
 }  // extern "C"
+
+// ---- host-link probe: what the platform gives one process for page-locked host <-> device copies.
+// bench.py runs it on every rank at once (barrier first) so that e2e can be stated as a fraction of
+// the link ceiling measured in the same run, under the same number of concurrent ranks.
+namespace ufair {
+struct LinkProbe {
+  void* host = nullptr;
+  void* dev = nullptr;
+  size_t cap = 0;
+  int device = -1;
+  cudaStream_t s_up = nullptr, s_down = nullptr;
+  void release() {
+    if (host) cudaFreeHost(host);
+    if (dev) cudaFree(dev);
+    if (s_up) cudaStreamDestroy(s_up);
+    if (s_down) cudaStreamDestroy(s_down);
+    host = dev = nullptr;
+    s_up = s_down = nullptr;
+    cap = 0;
+    device = -1;
+  }
+};
+static LinkProbe g_probe;
+
+static double wall_seconds() {
+  timespec ts;
+  clock_gettime(CLOCK_MONOTONIC, &ts);
+  return (double)ts.tv_sec + 1e-9 * (double)ts.tv_nsec;
+}
+}  // namespace ufair
+
+extern "C" int ufair_link_probe(int device, int64_t bytes, int32_t rows, int32_t reps, int32_t mode, double* gbs) {
+  using namespace ufair;
+  int prev = -1;
+  cudaGetDevice(&prev);
+  if (bytes <= 0) {  // release the probe's buffers
+    if (g_probe.device >= 0) {
+      cudaSetDevice(g_probe.device);
+      g_probe.release();
+      if (prev >= 0) cudaSetDevice(prev);
+    }
+    return UFAIR_OK;
+  }
+  if (!gbs || reps < 1 || mode < 0 || mode > 2 || rows < 0) return set_error(UFAIR_ERR_ARG, "ufair_link_probe: bad arguments");
+  if (rows > 1 && (bytes % rows) != 0) return set_error(UFAIR_ERR_ARG, "ufair_link_probe: bytes must be a multiple of rows");
+  CK(cudaSetDevice(device), "cudaSetDevice");
+  // each direction owns one half of both buffers; pitched copies need a host pitch of twice the row
+  const size_t need = (size_t)bytes * 4;
+  if (g_probe.device != device || g_probe.cap < need) {
+    g_probe.release();
+    cudaError_t e = cudaHostAlloc(&g_probe.host, need, cudaHostAllocDefault);
+    if (e == cudaSuccess) e = cudaMalloc(&g_probe.dev, need);
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&g_probe.s_up, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&g_probe.s_down, cudaStreamNonBlocking);
+    if (e != cudaSuccess) {
+      g_probe.release();
+      if (prev >= 0) cudaSetDevice(prev);
+      return cuda_error(e, "ufair_link_probe: allocation");
+    }
+    memset(g_probe.host, 0, need);  // touch: the pages exist before anything is timed
+    g_probe.cap = need;
+    g_probe.device = device;
+  }
+  char* h_up = (char*)g_probe.host;
+  char* h_down = h_up + 2 * (size_t)bytes;
+  char* d_up = (char*)g_probe.dev;
+  char* d_down = d_up + 2 * (size_t)bytes;
+  auto copy = [&](bool up, cudaStream_t s) -> cudaError_t {
+    if (rows > 1) {
+      const size_t w = (size_t)bytes / rows;
+      return up ? cudaMemcpy2DAsync(d_up, w, h_up, 2 * w, w, rows, cudaMemcpyHostToDevice, s)
+                : cudaMemcpy2DAsync(h_down, 2 * w, d_down, w, w, rows, cudaMemcpyDeviceToHost, s);
+    }
+    return up ? cudaMemcpyAsync(d_up, h_up, (size_t)bytes, cudaMemcpyHostToDevice, s)
+              : cudaMemcpyAsync(h_down, d_down, (size_t)bytes, cudaMemcpyDeviceToHost, s);
+  };
+  const bool up = mode != 1, down = mode != 0;
+  cudaError_t e = cudaSuccess;
+  if (up) e = copy(true, g_probe.s_up);  // warm-up
+  if (e == cudaSuccess && down) e = copy(false, g_probe.s_down);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(g_probe.s_up);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(g_probe.s_down);
+  double t_up = 0.0, t_down = 0.0;
+  const double t0 = wall_seconds();
+  for (int r = 0; r < reps && e == cudaSuccess; ++r) {
+    if (up) e = copy(true, g_probe.s_up);
+    if (e == cudaSuccess && down) e = copy(false, g_probe.s_down);
+  }
+  if (e == cudaSuccess && up) {
+    e = cudaStreamSynchronize(g_probe.s_up);
+    t_up = wall_seconds() - t0;
+  }
+  if (e == cudaSuccess && down) {
+    e = cudaStreamSynchronize(g_probe.s_down);
+    t_down = wall_seconds() - t0;
+  }
+  if (prev >= 0) cudaSetDevice(prev);
+  if (e != cudaSuccess) return cuda_error(e, "ufair_link_probe: copy");
+  const double gb = (double)bytes * reps / 1e9;
+  gbs[0] = up ? gb / t_up : 0.0;
+  gbs[1] = down ? gb / t_down : 0.0;
+  return UFAIR_OK;
+}

@@ -242,7 +242,11 @@ template <> struct Math<double> {
     int hi = __double2hiint(y), lo = __double2loint(y);
     // not a positive normal number (never on a physical trajectory): -inf for +-0 and subnormals
     // (flushed), NaN for negatives, y itself for +inf / NaN.  Kept tiny so it stays predicated.
+#ifndef UFAIR_EXP_LOG_NOSPECIAL  // experiment: what the special-case branch costs (basic-block splitting)
     if (__builtin_expect((unsigned)(hi - 0x00100000) >= 0x7fe00000u, 0))
+#else
+    if (false)
+#endif
       return (unsigned)(hi & 0x7fffffff) < 0x00100000u ? -INFINITY : (hi < 0 ? __longlong_as_double(0x7ff8000000000000ll) : y);
     // y = 2^e m with m in [sqrt(1/2), sqrt(2)): bias the high word so the exponent field rolls over
     // exactly at the mantissa of sqrt(2) (0x6a09e...), the fdlibm normalisation -- 4 integer ops

@@ -286,6 +286,15 @@ int ufair_workspace_destroy(ufair_workspace* ws);
 int ufair_run_host_f64(ufair_workspace* ws, const ufair_desc* d, uint64_t* hist, double* moments);
 int ufair_run_host_f32(ufair_workspace* ws, const ufair_desc* d, uint64_t* hist, double* moments);
 
+/* ---- host-link probe (measurement support: the ceiling bench.py states e2e against) ----
+ * Times `reps` copies of `bytes` bytes between a page-locked host buffer (allocated and kept by the
+ * probe) and device memory on `device`.  mode 0: host -> device; 1: device -> host; 2: both at once on
+ * two streams.  rows <= 1: contiguous cudaMemcpyAsync; rows > 1: one pitched cudaMemcpy2DAsync of `rows`
+ * rows per copy (host pitch = twice the row width: the shape of a member-chunk copy).  Wall clock from the
+ * first enqueue to the stream's completion.  gbs[0] = host -> device GB/s, gbs[1] = device -> host GB/s
+ * (0 for a direction the mode does not use).  bytes <= 0 releases the probe's buffers. */
+int ufair_link_probe(int device, int64_t bytes, int32_t rows, int32_t reps, int32_t mode, double* gbs);
+
 /* ---- device-math probe (test support): y[i] = op(x[i]) with the kernel's own math routines.
  * op: 0 decay(x)=1-exp(-x), 1 exp, 2 rcp, 3 sqrt, 4 log, 5 sinh. */
 int ufair_math_probe_f64(int op, const double* x, double* y, int64_t n, void* stream);

@@ -1,8 +1,9 @@
-"""ctypes loader for the C oracle (oracle/ufair_oracle.c).  TEST INFRASTRUCTURE ONLY.
+"""ctypes loader for the C oracle (oracle/ufair_oracle.c, ufair_oracle_fast.c).  TEST INFRASTRUCTURE ONLY.
 
 Same call shape as oracle.ufair_oracle.oxfair; used as the fast checker in tests/ and as the
-timed CPU baseline in bench.py.  Borrows only the descriptor *layout* from the product's
-ctypes binding (no CUDA code is touched).
+timed CPU baseline in bench.py.  The descriptor is the oracle's OWN (oracle/ufo.h, mirrored below):
+nothing is imported from the product package, so a field-order or constant slip in the product's
+binding cannot be common to both sides of a parity test.
 """
 from __future__ import annotations
 
@@ -12,18 +13,47 @@ import subprocess
 
 import numpy as np
 
-from fiveeqscm_b200 import _abi
-
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _SO = os.path.join(_HERE, "libufair_oracle.so")
 _LIB = None
 
+# ---- mirror of oracle/ufo.h -------------------------------------------------------------------
+E_MEMBER, E_SCENARIO = 0, 1
+FEXT_NONE, FEXT_SCENARIO, FEXT_MEMBER = 0, 1, 2
+OUT_C, OUT_RF, OUT_T, OUT_ALPHA, OUT_E = 1, 2, 4, 8, 16
+_pd, _pi = C.POINTER(C.c_double), C.POINTER(C.c_int32)
+
+
+def state_rows(n_gas: int) -> int:
+    return 5 * n_gas + 3
+
+
+class UfoDesc(C.Structure):
+    """`struct ufo_desc` of oracle/ufo.h (field order and types must match THAT header)."""
+    _fields_ = [
+        ("struct_size", C.c_uint64),
+        ("emissions", C.c_void_p), ("gas_params", C.c_void_p), ("thermal_params", C.c_void_p),
+        ("f_ext", C.c_void_p), ("e_scale", C.c_void_p), ("state_in", C.c_void_p), ("scen_idx", C.c_void_p),
+        ("out_C", C.c_void_p), ("out_RF", C.c_void_p), ("out_T", C.c_void_p), ("out_alpha", C.c_void_p),
+        ("out_E", C.c_void_p), ("state_out", C.c_void_p),
+        ("n_member", C.c_int64), ("ld_member", C.c_int64),
+        ("n_gas", C.c_int32), ("n_t", C.c_int32), ("n_scen", C.c_int32),
+        ("e_mode", C.c_int32), ("fext_mode", C.c_int32), ("alpha_mode", C.c_int32), ("newton_iters", C.c_int32),
+        ("t_mode", C.c_int32), ("out_mask", C.c_int32), ("conc_driven", C.c_int32),
+        ("dt", C.c_double), ("iirf_h", C.c_double), ("iirf_max", C.c_double),
+    ]
+
+    def __init__(self, **kw):
+        super().__init__()
+        self.struct_size = C.sizeof(UfoDesc)
+        for k, v in kw.items():
+            setattr(self, k, v)
+
 
 def build(force: bool = False) -> str:
-    src = os.path.join(_HERE, "ufair_oracle.c")
-    hdr = os.path.join(_HERE, "..", "include", "ufair.h")
+    srcs = [os.path.join(_HERE, f) for f in ("ufair_oracle.c", "ufair_oracle_fast.c", "ufo.h")]
     stale = (not os.path.exists(_SO)) or any(
-        os.path.exists(p) and os.path.getmtime(p) > os.path.getmtime(_SO) for p in (src, hdr))
+        os.path.exists(p) and os.path.getmtime(p) > os.path.getmtime(_SO) for p in srcs)
     if force or stale:
         subprocess.run(["make", "-C", _HERE, "-B" if force else "-s"], check=True,
                        stdout=subprocess.DEVNULL)
@@ -36,7 +66,9 @@ def lib():
         build()
         L = C.CDLL(_SO)
         L.ufo_run_f64.restype = C.c_int
-        L.ufo_run_f64.argtypes = [C.POINTER(_abi.UfairDesc), C.c_int]
+        L.ufo_run_f64.argtypes = [C.POINTER(UfoDesc), C.c_int]
+        L.ufo_run_blocked_f64.restype = C.c_int
+        L.ufo_run_blocked_f64.argtypes = [C.POINTER(UfoDesc), C.c_int]
         L.ufo_hfc_pulse.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64]
         L.ufo_g1g0.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_double, C.c_int,
                                C.c_void_p, C.c_void_p]
@@ -59,8 +91,12 @@ def _f64(a):
 def oxfair(emissions, gas_params, thermal_params, *, dt=1.0, scen_idx=None, e_scale=None, f_ext=None,
            fext_per_member=False, e_scenario=None, state_in=None, alpha_mode=0, newton_iters=0,
            iirf_max=None, iirf_h=100.0, t_mode=0, want_alpha=False, outputs=("C", "RF", "T"),
-           n_threads=0, conc_driven=0):
-    """C-oracle twin of oracle.ufair_oracle.oxfair (same arguments, float64 only)."""
+           n_threads=0, conc_driven=0, blocked=False):
+    """C-oracle twin of oracle.ufair_oracle.oxfair (same arguments, float64 only).
+
+    blocked=False: the textbook scalar loop (the parity checker).  blocked=True: the tiled, vectorised
+    rendering of the same loop (ufair_oracle_fast.c: the timed CPU baseline; a few ulp from the
+    scalar one, emission-driven runs only)."""
     E = _f64(emissions)
     gp = _f64(gas_params)
     tp = _f64(thermal_params)
@@ -87,24 +123,25 @@ def oxfair(emissions, gas_params, thermal_params, *, dt=1.0, scen_idx=None, e_sc
         out["alpha"] = np.empty((G, n_t, M))
     if conc_driven or "E" in want:
         out["E"] = np.empty((G, n_t, M))
-    out["state"] = np.empty((_abi.state_rows(G), M))
-    d = _abi.UfairDesc(
+    out["state"] = np.empty((state_rows(G), M))
+    d = UfoDesc(
         n_gas=G, n_t=n_t, n_member=M, ld_member=M,
         n_scen=(E.shape[2] if shared else (1 if fx is None or fext_per_member else fx.shape[1])),
-        e_mode=_abi.E_SCENARIO if shared else _abi.E_MEMBER,
-        fext_mode=(_abi.FEXT_NONE if fx is None else (_abi.FEXT_MEMBER if fext_per_member else _abi.FEXT_SCENARIO)),
+        e_mode=E_SCENARIO if shared else E_MEMBER,
+        fext_mode=(FEXT_NONE if fx is None else (FEXT_MEMBER if fext_per_member else FEXT_SCENARIO)),
         alpha_mode=alpha_mode, newton_iters=newton_iters, t_mode=t_mode,
-        out_mask=(_abi.OUT_C * ("C" in want) | _abi.OUT_RF * ("RF" in want) | _abi.OUT_T * ("T" in want)
-                  | _abi.OUT_ALPHA * ("alpha" in want) | _abi.OUT_E * ("E" in out)),
+        out_mask=(OUT_C * ("C" in want) | OUT_RF * ("RF" in want) | OUT_T * ("T" in want)
+                  | OUT_ALPHA * ("alpha" in want) | OUT_E * ("E" in out)),
         conc_driven=int(conc_driven), out_E=_p(out.get("E")),
         dt=dt, iirf_h=iirf_h, iirf_max=(0.0 if iirf_max is None else float(iirf_max)),
         emissions=_p(E), scen_idx=_p(si), e_scale=_p(es), f_ext=_p(fx), gas_params=_p(gp),
         thermal_params=_p(tp), state_in=_p(st_in),
         out_C=_p(out.get("C")), out_RF=_p(out.get("RF")), out_T=_p(out.get("T")),
         out_alpha=_p(out.get("alpha")), state_out=_p(out["state"]))
-    rc = lib().ufo_run_f64(C.byref(d), int(n_threads))
+    run = lib().ufo_run_blocked_f64 if blocked else lib().ufo_run_f64
+    rc = run(C.byref(d), int(n_threads))
     if rc < 0:
-        raise RuntimeError(f"ufo_run_f64 failed: {rc}")
+        raise RuntimeError(f"{'ufo_run_blocked_f64' if blocked else 'ufo_run_f64'} failed: {rc}")
     out["threads"] = rc
     return out
 

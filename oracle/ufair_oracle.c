@@ -4,8 +4,11 @@
  * TEST INFRASTRUCTURE -- NOT PART OF THE PRODUCT.  Only tests/, __graft_entry__.smoke() and
  * bench.py's cpu_baseline / --impl reference legs may load the library built from this file.
  *
- * It takes the same `ufair_desc` as libufair.so (include/ufair.h) but with HOST pointers, and
- * restates the algorithm in textbook form, one scalar member at a time, OpenMP over members.
+ * It takes its OWN descriptor (oracle/ufo.h: host pointers, the oracle's own field order and
+ * constants -- deliberately not the product's include/ufair.h, so that a layout mistake on either
+ * side shows up as a parity failure instead of cancelling out) and restates the algorithm in
+ * textbook form, one scalar member at a time, OpenMP over members.  ufair_oracle_fast.c holds the
+ * blocked / vectorised rendering of the same loop that bench.py times as the CPU baseline.
  *
  * Parity status (same as oracle/ufair_oracle.py, which this file mirrors function by function):
  *   - ufo_hfc_pulse: PINNED to reference U_FaIR/concentrations.py:4-5 and the golden vector in
@@ -22,7 +25,7 @@
 #include <omp.h>
 #endif
 
-#include "../include/ufair.h"
+#include "ufo.h"
 
 /* reference U_FaIR/concentrations.py:5 : emissions[0] * np.exp(-time), already broadcast */
 int ufo_hfc_pulse(const double* e0, const double* time, double* out, int64_t n) {
@@ -42,7 +45,7 @@ static double g_0(const double a[4], const double tau[4], double h, double g1, i
   double s = 0.0;
   for (int i = 0; i < 4; ++i) s += a[i] * tau[i] * (1.0 - exp(-h / tau[i]));
   s /= g1;
-  return alpha_mode == UFAIR_ALPHA_SINH ? 1.0 / sinh(s) : exp(-s);
+  return alpha_mode == UFO_ALPHA_SINH ? 1.0 / sinh(s) : exp(-s);
 }
 
 int ufo_g1g0(const double* a, const double* tau, int64_t n, int64_t ld, double h, int alpha_mode,
@@ -72,10 +75,10 @@ int ufo_kq(const double* tcr, const double* ecs, const double* d1, const double*
 /* alpha_val (.coveragerc:17) */
 static double alpha_val(double iirf, double g0, double g1, const double a[4], const double tau[4],
                         int alpha_mode, int newton_iters, double h) {
-  if (alpha_mode == UFAIR_ALPHA_ONE) return 1.0;
-  if (alpha_mode == UFAIR_ALPHA_SINH) return g0 * sinh(iirf / g1);
+  if (alpha_mode == UFO_ALPHA_ONE) return 1.0;
+  if (alpha_mode == UFO_ALPHA_SINH) return g0 * sinh(iirf / g1);
   double alpha = g0 * exp(iirf / g1);
-  if (alpha_mode == UFAIR_ALPHA_NEWTON) {
+  if (alpha_mode == UFO_ALPHA_NEWTON) {
     for (int k = 0; k < newton_iters; ++k) {
       double f = -iirf, fp = 0.0;
       for (int i = 0; i < 4; ++i) {
@@ -91,7 +94,7 @@ static double alpha_val(double iirf, double g0, double g1, const double a[4], co
 }
 
 /* oxfair (.coveragerc:19) for one member; step_conc / step_forc / step_temp inline and labelled */
-static void run_member(const ufair_desc* d, int64_t m) {
+static void run_member(const ufo_desc* d, int64_t m) {
   const int G = d->n_gas, n_t = d->n_t;
   const int64_t ld = d->ld_member;
   const double* E = (const double*)d->emissions;
@@ -104,11 +107,11 @@ static void run_member(const ufair_desc* d, int64_t m) {
   const int clamp = (d->iirf_max > 0.0 && isfinite(d->iirf_max));
   const int s = d->scen_idx ? d->scen_idx[m] : 0;
 
-  double a[UFAIR_MAX_GAS][4], tau[UFAIR_MAX_GAS][4], g1[UFAIR_MAX_GAS], g0[UFAIR_MAX_GAS];
-  double R[UFAIR_MAX_GAS][4], Gc[UFAIR_MAX_GAS], S[2], Tprev;
-#define GP(g, r) gp[((int64_t)(g) * UFAIR_GP_COUNT + (r)) * ld + m]
+  double a[UFO_MAX_GAS][4], tau[UFO_MAX_GAS][4], g1[UFO_MAX_GAS], g0[UFO_MAX_GAS];
+  double R[UFO_MAX_GAS][4], Gc[UFO_MAX_GAS], S[2], Tprev;
+#define GP(g, r) gp[((int64_t)(g) * UFO_GP_COUNT + (r)) * ld + m]
   for (int g = 0; g < G; ++g) {
-    for (int i = 0; i < 4; ++i) { a[g][i] = GP(g, UFAIR_GP_A0 + i); tau[g][i] = GP(g, UFAIR_GP_TAU0 + i); }
+    for (int i = 0; i < 4; ++i) { a[g][i] = GP(g, UFO_GP_A0 + i); tau[g][i] = GP(g, UFO_GP_TAU0 + i); }
     g1[g] = g_1(a[g], tau[g], h);
     g0[g] = g_0(a[g], tau[g], h, g1[g], d->alpha_mode);
     for (int i = 0; i < 4; ++i) R[g][i] = sin_ ? sin_[(5 * g + i) * ld + m] : 0.0;
@@ -117,30 +120,30 @@ static void run_member(const ufair_desc* d, int64_t m) {
   S[0] = sin_ ? sin_[(5 * G + 0) * ld + m] : 0.0;
   S[1] = sin_ ? sin_[(5 * G + 1) * ld + m] : 0.0;
   Tprev = sin_ ? sin_[(5 * G + 2) * ld + m] : 0.0;
-  const double q[2] = {tp[UFAIR_TP_Q1 * ld + m], tp[UFAIR_TP_Q2 * ld + m]};
-  const double dd[2] = {tp[UFAIR_TP_D1 * ld + m], tp[UFAIR_TP_D2 * ld + m]};
+  const double q[2] = {tp[UFO_TP_Q1 * ld + m], tp[UFO_TP_Q2 * ld + m]};
+  const double dd[2] = {tp[UFO_TP_D1 * ld + m], tp[UFO_TP_D2 * ld + m]};
 
-  double* oC = (d->out_mask & UFAIR_OUT_C) ? (double*)d->out_C : NULL;
-  double* oF = (d->out_mask & UFAIR_OUT_RF) ? (double*)d->out_RF : NULL;
-  double* oT = (d->out_mask & UFAIR_OUT_T) ? (double*)d->out_T : NULL;
-  double* oA = (d->out_mask & UFAIR_OUT_ALPHA) ? (double*)d->out_alpha : NULL;
-  double* oE = (d->out_mask & UFAIR_OUT_E) ? (double*)d->out_E : NULL;
+  double* oC = (d->out_mask & UFO_OUT_C) ? (double*)d->out_C : NULL;
+  double* oF = (d->out_mask & UFO_OUT_RF) ? (double*)d->out_RF : NULL;
+  double* oT = (d->out_mask & UFO_OUT_T) ? (double*)d->out_T : NULL;
+  double* oA = (d->out_mask & UFO_OUT_ALPHA) ? (double*)d->out_alpha : NULL;
+  double* oE = (d->out_mask & UFO_OUT_E) ? (double*)d->out_E : NULL;
 
   for (int t = 0; t < n_t; ++t) {
     double Ftot = 0.0;
     for (int g = 0; g < G; ++g) {
       double e;
-      if (d->e_mode == UFAIR_E_SCENARIO) {
+      if (d->e_mode == UFO_E_SCENARIO) {
         e = E[((int64_t)g * n_t + t) * d->n_scen + s];
         if (esc) e = e * esc[(int64_t)g * ld + m];
       } else {
         e = E[((int64_t)g * n_t + t) * ld + m];
       }
-      const double c = GP(g, UFAIR_GP_EMIS2CONC), C0 = GP(g, UFAIR_GP_C0);
+      const double c = GP(g, UFO_GP_EMIS2CONC), C0 = GP(g, UFO_GP_C0);
       /* alpha from the state at t-1 */
       double Ga = (R[g][0] + R[g][1] + R[g][2] + R[g][3]) / c;
-      double iirf = GP(g, UFAIR_GP_R0) + GP(g, UFAIR_GP_RU) * (Gc[g] - Ga) + GP(g, UFAIR_GP_RT) * Tprev +
-                    GP(g, UFAIR_GP_RA) * Ga;
+      double iirf = GP(g, UFO_GP_R0) + GP(g, UFO_GP_RU) * (Gc[g] - Ga) + GP(g, UFO_GP_RT) * Tprev +
+                    GP(g, UFO_GP_RA) * Ga;
       if (clamp && iirf > d->iirf_max) iirf = d->iirf_max;
       double alpha = alpha_val(iirf, g0[g], g1[g], a[g], tau[g], d->alpha_mode, d->newton_iters, h);
       /* concentration-driven gas: the input row is the target C; step_conc is linear in E, so
@@ -167,7 +170,7 @@ static void run_member(const ufair_desc* d, int64_t m) {
       double C = C0 + sumR;
       /* step_forc (.coveragerc:13) */
       /* a term whose coefficient is exactly zero contributes exactly zero (C0 = 0 gases) */
-      const double f1 = GP(g, UFAIR_GP_F1), f2 = GP(g, UFAIR_GP_F2), f3 = GP(g, UFAIR_GP_F3);
+      const double f1 = GP(g, UFO_GP_F1), f2 = GP(g, UFO_GP_F2), f3 = GP(g, UFO_GP_F3);
       double logt = (f1 != 0.0) ? f1 * log(C / C0) : 0.0;
       double sqrtt = (f3 != 0.0) ? f3 * (sqrt(C) - sqrt(C0)) : 0.0;
       double F = logt + f2 * (C - C0) + sqrtt;
@@ -178,14 +181,14 @@ static void run_member(const ufair_desc* d, int64_t m) {
       if (oE) oE[o] = e;
       Ftot = Ftot + F;
     }
-    if (d->fext_mode == UFAIR_FEXT_SCENARIO) Ftot = Ftot + fx[(int64_t)t * d->n_scen + s];
-    else if (d->fext_mode == UFAIR_FEXT_MEMBER) Ftot = Ftot + fx[(int64_t)t * ld + m];
+    if (d->fext_mode == UFO_FEXT_SCENARIO) Ftot = Ftot + fx[(int64_t)t * d->n_scen + s];
+    else if (d->fext_mode == UFO_FEXT_MEMBER) Ftot = Ftot + fx[(int64_t)t * ld + m];
     /* step_temp (.coveragerc:14) */
     double T = 0.0;
     for (int j = 0; j < 2; ++j) {
       double dec = exp(-dt / dd[j]);
       double Sn = q[j] * Ftot * (1.0 - dec) + S[j] * dec;
-      T += (d->t_mode == UFAIR_T_MID) ? (S[j] + Sn) / 2.0 : Sn;
+      T += (d->t_mode == UFO_T_MID) ? (S[j] + Sn) / 2.0 : Sn;
       S[j] = Sn;
     }
     if (oT) oT[(int64_t)t * ld + m] = T;
@@ -205,9 +208,9 @@ static void run_member(const ufair_desc* d, int64_t m) {
 }
 
 /* n_threads <= 0: all the OpenMP runtime offers. Returns the thread count used. */
-int ufo_run_f64(const ufair_desc* d, int n_threads) {
-  if (!d || d->struct_size != sizeof(ufair_desc)) return UFAIR_ERR_ARG;
-  if (d->n_gas < 1 || d->n_gas > UFAIR_MAX_GAS || d->n_t < 0 || d->n_member < 0) return UFAIR_ERR_ARG;
+int ufo_run_f64(const ufo_desc* d, int n_threads) {
+  if (!d || d->struct_size != sizeof(ufo_desc)) return -1;
+  if (d->n_gas < 1 || d->n_gas > UFO_MAX_GAS || d->n_t < 0 || d->n_member < 0) return -1;
   int used = 1;
 #ifdef _OPENMP
   if (n_threads <= 0) n_threads = omp_get_max_threads();

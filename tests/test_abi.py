@@ -68,11 +68,52 @@ def test_argument_errors_are_reported_not_fatal(built):
         _abi.check(L.ufair_run_f32(ctypes.byref(d), None))
 
 
-def test_oracle_struct_layout_matches_c(built):
-    # the C oracle checks struct_size against its own sizeof(ufair_desc): same header, same layout
+def _c_layout(header, struct, fields, tmp_path):
+    """sizeof(struct) and offsetof every field, as the C compiler lays the header's struct out."""
+    import subprocess
+    src = tmp_path / f"layout_{struct}.c"
+    exe = tmp_path / f"layout_{struct}"
+    body = "".join(f'  printf("{f} %zu\\n", offsetof({struct}, {f}));\n' for f in fields)
+    src.write_text(f'#include <stddef.h>\n#include <stdio.h>\n#include "{header}"\nint main(void) {{\n'
+                   f'  printf("sizeof %zu\\n", sizeof({struct}));\n{body}  return 0;\n}}\n')
+    subprocess.run(["gcc", "-std=c11", "-o", str(exe), str(src)], check=True)
+    out = subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout.split()
+    return dict(zip(out[0::2], (int(v) for v in out[1::2])))
+
+
+@pytest.mark.parametrize("which", ["ufair_desc", "ufair_sampler", "ufo_desc"])
+def test_ctypes_mirrors_match_the_c_headers_field_by_field(which, tmp_path):
+    """Each binding is checked against ITS OWN header by the C compiler (offsetof every field), so the
+    product's descriptor (include/ufair.h <-> _abi.UfairDesc) and the oracle's (oracle/ufo.h <->
+    c_oracle.UfoDesc) are each right on their own -- they share no code that could be wrong twice."""
     from oracle import c_oracle
-    d = _abi.UfairDesc(n_gas=1, n_t=0, n_member=0, ld_member=0)
+    header, cls = {"ufair_desc": (HEADER, _abi.UfairDesc), "ufair_sampler": (HEADER, _abi.UfairSampler),
+                   "ufo_desc": (os.path.join(ROOT, "oracle", "ufo.h"), c_oracle.UfoDesc)}[which]
+    names = [f[0] for f in cls._fields_]
+    lay = _c_layout(header, which, names, tmp_path)
+    assert lay["sizeof"] == ctypes.sizeof(cls)
+    for n in names:
+        assert lay[n] == getattr(cls, n).offset, f"{which}.{n}: C offset {lay[n]} != ctypes {getattr(cls, n).offset}"
+    # and the header has no field the binding forgot
+    src = re.sub(r"/\*.*?\*/", "", open(header).read(), flags=re.S)
+    body = re.search(r"typedef struct %s \{(.*?)\} %s;" % (which, which), src, flags=re.S).group(1)
+    declared = [re.search(r"(\w+)\s*(?:\[[^\]]*\])*\s*$", part.strip()).group(1)
+                for stmt in body.split(";") if stmt.strip() for part in stmt.split(",")]
+    assert sorted(declared) == sorted(names)
+
+
+def test_oracle_descriptor_is_its_own(built):
+    """oracle/c_oracle.py must not borrow the product's binding, and the C oracle must not include the
+    product's header (a layout mistake would be common-mode)."""
+    from oracle import c_oracle
+    assert "fiveeqscm_b200" not in open(os.path.join(ROOT, "oracle", "c_oracle.py")).read().replace(
+        "fiveeqscm_b200/_abi.py", "")
+    for f in ("ufair_oracle.c", "ufair_oracle_fast.c", "ufo.h"):
+        assert "ufair.h" not in re.sub(r"/\*.*?\*/", "", open(os.path.join(ROOT, "oracle", f)).read(), flags=re.S)
+    d = c_oracle.UfoDesc(n_gas=1, n_t=0, n_member=0, ld_member=0)
     assert c_oracle.lib().ufo_run_f64(ctypes.byref(d), 1) >= 1
+    d.struct_size = 8
+    assert c_oracle.lib().ufo_run_f64(ctypes.byref(d), 1) < 0
 
 
 def test_product_never_imports_the_oracle():

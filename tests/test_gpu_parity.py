@@ -51,6 +51,23 @@ def _golden_cases():
     return [(n, z[f"{n}__emissions"], z[f"{n}__time"], float(z[f"{n}__lifetime"]), z[f"{n}__expected"]) for n in names]
 
 
+def test_reference_test_file_itself_passes_unmodified(api):
+    """The reference's own test FILE (tests/unit/test_hfcs.py, vendored byte for byte as
+    tests/golden/ref_test_hfcs.py -- sha256 pinned in tests/test_host_logic.py), run by pytest in a
+    fresh interpreter against this repo's U_FaIR package: the drop-in claim of SURVEY.md 8b."""
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, PYTHONPATH=root + os.pathsep + os.environ.get("PYTHONPATH", ""))
+    r = subprocess.run([sys.executable, "-m", "pytest", "-q", "-p", "no:cacheprovider", "-c", os.devnull, "--rootdir", root,
+                        os.path.join(root, "tests", "golden", "ref_test_hfcs.py")],
+                       cwd=root, env=env, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0 and "1 passed" in r.stdout, r.stdout + r.stderr
+    # ... and it really was this repo's CUDA implementation that answered
+    import U_FaIR.concentrations as uc
+    assert os.path.dirname(os.path.abspath(uc.__file__)) == os.path.join(root, "U_FaIR")
+
+
 def test_reference_test_reads_unchanged(api):
     # reference tests/unit/test_hfcs.py:5-13, through the drop-in module path
     from U_FaIR.concentrations import calculate_hfc_conc
