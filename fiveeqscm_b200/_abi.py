@@ -150,6 +150,8 @@ SIGNATURES = {
     "ufair_stats_pass_f64": (C.c_int, [C.POINTER(UfairDesc), _vp]),
     "ufair_stats_pass_f32": (C.c_int, [C.POINTER(UfairDesc), _vp]),
     "ufair_stats_finalize": (C.c_int, [C.POINTER(UfairDesc), _vp, _vp, _vp]),
+    "ufair_stats_finalize_packed": (C.c_int, [C.POINTER(UfairDesc), _vp, _vp, _vp]),
+    "ufair_stats_unpack": (C.c_int, [_vp, _vp, _i32, _i32, _vp, _vp, _vp]),
     "ufair_hist_percentiles": (C.c_int, [_vp, _i32, _i32, _dbl, _dbl, _vp, _i32, _vp, _vp]),
     "ufair_g1g0_f64": (C.c_int, [_vp, _vp, _i64, _i64, _dbl, _i32, _vp, _vp, _vp]),
     "ufair_kq_f64": (C.c_int, [_vp, _vp, _vp, _vp, _dbl, _i64, _vp, _vp, _vp]),
@@ -160,7 +162,7 @@ SIGNATURES = {
     "ufair_workspace_destroy": (C.c_int, [_vp]),
     "ufair_run_host_f64": (C.c_int, [_vp, C.POINTER(UfairDesc), _vp, _vp]),
     "ufair_run_host_f32": (C.c_int, [_vp, C.POINTER(UfairDesc), _vp, _vp]),
-    "ufair_link_probe": (C.c_int, [C.c_int, _i64, _i32, _i32, _i32, _pd]),
+    "ufair_link_probe": (C.c_int, [C.c_int, _i64, _i64, _i32, _i32, _pd, _pd]),
     "ufair_math_probe_f64": (C.c_int, [C.c_int, _vp, _vp, _i64, _vp]),
     "ufair_math_probe_f32": (C.c_int, [C.c_int, _vp, _vp, _i64, _vp]),
     "ufair_peak_fp64": (C.c_int, [C.c_int, _pd, _pd, _vp]),

@@ -251,7 +251,7 @@ def run_ensemble(emissions, gas_params, thermal_params, *, dt=1.0, scen_idx=None
                      precision, return_state, chunk_members, workspace, out, gas_form, conc_driven)
 
 
-def _shapes(E_shape, gp_shape, tp_shape, scen_idx, fext_shape, fext_per_member):
+def _shapes(E_shape, gp_shape, tp_shape, scen_idx, fext_shape, fext_per_member, e_scale_shape=None):
     if len(E_shape) != 3 or len(gp_shape) != 3 or len(tp_shape) != 2:
         raise ValueError("emissions must be [G][n_t][M|S], gas_params [G][17][M], thermal_params [4][M]")
     G, n_t = E_shape[0], E_shape[1]
@@ -260,8 +260,17 @@ def _shapes(E_shape, gp_shape, tp_shape, scen_idx, fext_shape, fext_per_member):
         raise ValueError(f"n_gas must be 1..{_abi.MAX_GAS}")
     if gp_shape[0] != G or gp_shape[1] != _abi.GP_COUNT or tuple(tp_shape) != (_abi.TP_COUNT, M):
         raise ValueError("gas_params must be [G][17][M] and thermal_params [4][M]")
-    e_scen = scen_idx is not None or E_shape[2] != M
+    # scenario-shared emissions are explicit: a scen_idx, or a single column every member shares
+    e_scen = scen_idx is not None or (E_shape[2] == 1 and M != 1)
+    if not e_scen and E_shape[2] != M:
+        raise ValueError(f"emissions last axis is {E_shape[2]}: per-member emissions need {M} columns (one per member); "
+                         "scenario-shared emissions [G][n_t][S] need scen_idx [M] (or S == 1)")
     n_scen = E_shape[2] if e_scen else 1
+    if e_scale_shape is not None:
+        if not e_scen:
+            raise ValueError("e_scale applies to scenario-shared emissions only")
+        if tuple(e_scale_shape) != (G, M):
+            raise ValueError(f"e_scale must be [G][M] = ({G}, {M}), got {tuple(e_scale_shape)}")
     fext_mode = _abi.FEXT_NONE
     if fext_shape is not None:
         if fext_per_member:
@@ -299,8 +308,10 @@ class DevicePlan:
         self.device, self.precision, self.stats = dev, precision, stats
         fshape = None if f_ext is None else tuple(f_ext.shape)
         G, n_t, M, e_scen, n_scen, fext_mode = _shapes(tuple(E.shape), tuple(gp.shape), tuple(tp.shape), scen_idx,
-                                                       fshape, fext_per_member)
+                                                       fshape, fext_per_member,
+                                                       None if e_scale is None else tuple(e_scale.shape))
         self.n_gas, self.n_t, self.n_member = G, n_t, M
+        self.scen_idx = None
         ld = _round_up(max(M, 1), 16 // es)
 
         def member_rows(x, name):  # [..][M] -> contiguous [..][ld] of the run dtype, 16-byte aligned rows
@@ -334,9 +345,8 @@ class DevicePlan:
                 raise ValueError("scen_idx out of range")
             keep.append(si)
             d.scen_idx = si.data_ptr()
+            self.scen_idx = si    # the plan's own copy: callers that re-launch may overwrite it in place
         if e_scale is not None:
-            if not e_scen:
-                raise ValueError("e_scale applies to scenario-shared emissions only")
             esd = member_rows(e_scale, "e_scale")
             keep.append(esd)
             d.e_scale = esd.data_ptr()
@@ -474,7 +484,8 @@ def _run_host(torch, E, gp, tp, dt, scen_idx, e_scale, f_ext, fext_per_member, s
 
     E, gp, tp, e_scale, f_ext, state_in = (arr(x) for x in (E, gp, tp, e_scale, f_ext, state_in))
     fshape = None if f_ext is None else f_ext.shape
-    G, n_t, M, e_scen, n_scen, fext_mode = _shapes(E.shape, gp.shape, tp.shape, scen_idx, fshape, fext_per_member)
+    G, n_t, M, e_scen, n_scen, fext_mode = _shapes(E.shape, gp.shape, tp.shape, scen_idx, fshape, fext_per_member,
+                                                   None if e_scale is None else e_scale.shape)
     auto_form = isinstance(gas_form, str)
     if auto_form and gas_form != "auto":
         raise ValueError("gas_form must be 'auto', None or one entry per gas")
@@ -489,8 +500,7 @@ def _run_host(torch, E, gp, tp, dt, scen_idx, e_scale, f_ext, fext_per_member, s
         keep.append(si)
         d.scen_idx = si.ctypes.data
     if e_scale is not None:
-        if not e_scen:
-            raise ValueError("e_scale applies to scenario-shared emissions only")
+        keep.append(e_scale)
         d.e_scale = e_scale.ctypes.data
     if f_ext is not None:
         if not fext_per_member and f_ext.size == n_t and n_scen > 1:

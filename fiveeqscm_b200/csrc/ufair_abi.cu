@@ -39,6 +39,10 @@ int validate_desc(const ufair_desc* d, size_t elem) {
     return set_error(UFAIR_ERR_ARG, "n_gas %d outside 1..%d", d->n_gas, UFAIR_MAX_GAS);
   if (d->n_t < 0 || d->n_member < 0) return set_error(UFAIR_ERR_ARG, "negative n_t / n_member");
   if (d->ld_member < d->n_member) return set_error(UFAIR_ERR_ARG, "ld_member < n_member");
+  // TMA box coordinates and the warp index arithmetic are 32-bit: one launch takes at most 2^31 - 1 members per row
+  if (d->ld_member > (int64_t)INT32_MAX)
+    return set_error(UFAIR_ERR_ARG, "ld_member %lld > %d: split the member axis over several calls", (long long)d->ld_member,
+                     INT32_MAX);
   if (d->n_member > 0 && (d->ld_member * (int64_t)elem) % 16 != 0)
     return set_error(UFAIR_ERR_ALIGN, "ld_member %lld: rows must be a multiple of 16 bytes", (long long)d->ld_member);
   if (d->e_mode != UFAIR_E_MEMBER && d->e_mode != UFAIR_E_SCENARIO) return set_error(UFAIR_ERR_ARG, "bad e_mode");
@@ -395,6 +399,51 @@ __global__ void stats_finalize_kernel(const unsigned int* hp, const double* mp, 
   }
 }
 
+// The same fold, written in the layout the cross-GPU reduction wants: ONE buffer that is summed
+// (sums[row][0 .. bins) = the counts as doubles -- integers below 2^53 add exactly in any order, so the
+// reduced histogram stays bitwise independent of the GPU count --, sums[row][bins] = sum T,
+// sums[row][bins + 1] = sum T^2) and ONE buffer that is max-reduced (ext[row] = {max T, -min T}).
+__global__ void stats_finalize_packed_kernel(const unsigned int* hp, const double* mp, int copies, int rows, int bins,
+                                             double* sums, double* ext) {
+  const int pitch = bins + 2;
+  const size_t n = (size_t)rows * bins;
+  const size_t i0 = (size_t)blockIdx.x * blockDim.x + threadIdx.x, stride = (size_t)gridDim.x * blockDim.x;
+  for (size_t i = i0; i < n; i += stride) {
+    unsigned long long s = 0;
+    for (int c = 0; c < copies; ++c) s += hp[(size_t)c * n + i];
+    sums[(i / bins) * pitch + (i % bins)] = (double)s;
+  }
+  for (size_t r = i0; r < (size_t)rows; r += stride) {
+    double sm = 0.0, ss = 0.0, mn = INFINITY, mx = -INFINITY;
+    for (int c = 0; c < copies; ++c) {  // fixed order: deterministic
+      const double* p = mp + ((size_t)c * rows + r) * UFAIR_MOM_COUNT;
+      sm += p[UFAIR_MOM_SUM];
+      ss += p[UFAIR_MOM_SUMSQ];
+      mn = fmin(mn, p[UFAIR_MOM_MIN]);
+      mx = fmax(mx, p[UFAIR_MOM_MAX]);
+    }
+    sums[r * pitch + bins] = sm;
+    sums[r * pitch + bins + 1] = ss;
+    ext[2 * r] = mx;
+    ext[2 * r + 1] = -mn;
+  }
+}
+
+__global__ void stats_unpack_kernel(const double* sums, const double* ext, int rows, int bins, unsigned long long* hist,
+                                    double* mom) {
+  const int pitch = bins + 2;
+  const size_t n = (size_t)rows * bins;
+  const size_t i0 = (size_t)blockIdx.x * blockDim.x + threadIdx.x, stride = (size_t)gridDim.x * blockDim.x;
+  for (size_t i = i0; i < n; i += stride) hist[i] = (unsigned long long)sums[(i / bins) * pitch + (i % bins)];
+  for (size_t r = i0; r < (size_t)rows; r += stride) {
+    double* o = mom + r * UFAIR_MOM_COUNT;
+    o[UFAIR_MOM_SUM] = sums[r * pitch + bins];
+    o[UFAIR_MOM_SUMSQ] = sums[r * pitch + bins + 1];
+    o[UFAIR_MOM_MAX] = ext[2 * r];
+    o[UFAIR_MOM_MIN] = -ext[2 * r + 1];
+  }
+}
+
 // one thread per (row, percentile): walk the row's CDF (exact integers), interpolate inside the bin.
 // Same operations in the same order as oracle/ufair_oracle.py percentiles_from_hist (no FMA).
 __global__ void percentiles_kernel(const unsigned long long* __restrict__ hist, int rows, int bins, double lo, double hi,
@@ -574,11 +623,12 @@ int ufair_kernel_variant(const ufair_desc* d, int32_t elem_size, uint32_t* form,
   const int rc = validate_desc(d, (size_t)elem_size);
   if (rc != UFAIR_OK) return rc;
   const unsigned f = pick_form(d);
-  const int g = gases_per_lane(elem_size, d->n_gas, f);
+  const int var = wants_inverse(d) ? (int)kVarInverse : plain_variant(d);
+  const int g = runtime_gases_per_lane(d, elem_size, f, var);
   if (form) *form = f;
   if (gpl) *gpl = g;
   if (mw) *mw = members_per_warp(elem_size, d->n_gas, g);
-  if (loop) *loop = wants_inverse(d) ? (int)kVarInverse : plain_variant(d);
+  if (loop) *loop = var;
   return UFAIR_OK;
 }
 
@@ -600,6 +650,26 @@ int ufair_stats_finalize(const ufair_desc* d, uint64_t* hist, double* moments, v
                                                                (unsigned long long*)hist, moments);
   cudaError_t e = cudaGetLastError();
   return e == cudaSuccess ? UFAIR_OK : cuda_error(e, "stats_finalize_kernel");
+}
+
+int ufair_stats_finalize_packed(const ufair_desc* d, double* sums, double* ext, void* stream) {
+  int rc = check_stats_desc(d);
+  if (rc != UFAIR_OK) return rc;
+  if (!sums || !ext) return set_error(UFAIR_ERR_ARG, "sums / ext output is NULL");
+  stats_finalize_packed_kernel<<<592, 256, 0, (cudaStream_t)stream>>>(d->hist_private, d->moments_private, d->hist_copies,
+                                                                      d->hist_rows, d->hist_bins, sums, ext);
+  cudaError_t e = cudaGetLastError();
+  return e == cudaSuccess ? UFAIR_OK : cuda_error(e, "stats_finalize_packed_kernel");
+}
+
+int ufair_stats_unpack(const double* sums, const double* ext, int32_t rows, int32_t bins, uint64_t* hist, double* moments,
+                       void* stream) {
+  if (rows < 0 || bins < 1) return set_error(UFAIR_ERR_ARG, "bad rows / bins");
+  if (rows == 0) return UFAIR_OK;
+  if (!sums || !ext || !hist || !moments) return set_error(UFAIR_ERR_ARG, "NULL pointer");
+  stats_unpack_kernel<<<592, 256, 0, (cudaStream_t)stream>>>(sums, ext, rows, bins, (unsigned long long*)hist, moments);
+  cudaError_t e = cudaGetLastError();
+  return e == cudaSuccess ? UFAIR_OK : cuda_error(e, "stats_unpack_kernel");
 }
 
 int ufair_g1g0_f64(const double* a, const double* tau, int64_t n, int64_t ld, double h, int32_t mode, double* g1,

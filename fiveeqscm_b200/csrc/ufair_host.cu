@@ -18,6 +18,19 @@
 
 namespace ufair {
 
+// switch to `device` for the lifetime of the guard, then back to whatever the caller had current
+struct DeviceGuard {
+  int prev = -1;
+  cudaError_t err = cudaSuccess;
+  explicit DeviceGuard(int device) {
+    if (cudaGetDevice(&prev) != cudaSuccess) prev = -1;
+    if (prev != device) err = cudaSetDevice(device);
+  }
+  ~DeviceGuard() {
+    if (prev >= 0) cudaSetDevice(prev);
+  }
+};
+
 struct DevBuf {
   void* p = nullptr;
   size_t cap = 0;
@@ -209,7 +222,10 @@ template <typename Real> static int run_host(ufair_workspace* ws, const ufair_de
   if (h->n_member == 0 || h->n_t == 0) return UFAIR_OK;
   if (!h->emissions || !h->gas_params || !h->thermal_params)
     return set_error(UFAIR_ERR_ARG, "emissions / gas_params / thermal_params must not be NULL");
-  CK(cudaSetDevice(ws->device), "cudaSetDevice");
+  if (h->ld_member > (int64_t)INT32_MAX || (uint64_t)h->ld_member * sizeof(Real) > (uint64_t)INT32_MAX * 8u)
+    return set_error(UFAIR_ERR_ARG, "ld_member %lld is too large for one call: split the member axis", (long long)h->ld_member);
+  DeviceGuard guard(ws->device);  // the caller's current device is restored on every return path
+  if (guard.err != cudaSuccess) return cuda_error(guard.err, "cudaSetDevice");
 
   const size_t es = sizeof(Real);
   const int G = h->n_gas, n_t = h->n_t;
@@ -290,7 +306,8 @@ int ufair_workspace_create(int device, int64_t chunk_members, ufair_workspace** 
   if (!ws) return set_error(UFAIR_ERR_NOMEM, "out of host memory");
   ws->device = device;
   ws->chunk = chunk_members;
-  cudaError_t e = cudaSetDevice(device);
+  DeviceGuard guard(device);
+  cudaError_t e = guard.err;
   if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&ws->s_in, cudaStreamNonBlocking);
   if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&ws->s_run, cudaStreamNonBlocking);
   if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&ws->s_out, cudaStreamNonBlocking);
@@ -309,7 +326,7 @@ int ufair_workspace_create(int device, int64_t chunk_members, ufair_workspace** 
 
 int ufair_workspace_destroy(ufair_workspace* ws) {
   if (!ws) return UFAIR_OK;
-  cudaSetDevice(ws->device);
+  DeviceGuard guard(ws->device);
   for (int i = 0; i < 2; ++i) {
     for (int j = 0; j < B_COUNT; ++j) ws->st[i].b[j].release();
     if (ws->st[i].in_done) cudaEventDestroy(ws->st[i].in_done);
@@ -368,23 +385,24 @@ static double wall_seconds() {
 }
 }  // namespace ufair
 
-extern "C" int ufair_link_probe(int device, int64_t bytes, int32_t rows, int32_t reps, int32_t mode, double* gbs) {
+extern "C" int ufair_link_probe(int device, int64_t bytes_up, int64_t bytes_down, int32_t rows, int32_t reps, double* gbs,
+                                double* seconds) {
   using namespace ufair;
-  int prev = -1;
-  cudaGetDevice(&prev);
-  if (bytes <= 0) {  // release the probe's buffers
+  if (bytes_up <= 0 && bytes_down <= 0) {  // release the probe's buffers
     if (g_probe.device >= 0) {
-      cudaSetDevice(g_probe.device);
+      DeviceGuard guard(g_probe.device);
       g_probe.release();
-      if (prev >= 0) cudaSetDevice(prev);
     }
     return UFAIR_OK;
   }
-  if (!gbs || reps < 1 || mode < 0 || mode > 2 || rows < 0) return set_error(UFAIR_ERR_ARG, "ufair_link_probe: bad arguments");
-  if (rows > 1 && (bytes % rows) != 0) return set_error(UFAIR_ERR_ARG, "ufair_link_probe: bytes must be a multiple of rows");
-  CK(cudaSetDevice(device), "cudaSetDevice");
-  // each direction owns one half of both buffers; pitched copies need a host pitch of twice the row
-  const size_t need = (size_t)bytes * 4;
+  if (!gbs || reps < 1 || rows < 0 || bytes_up < 0 || bytes_down < 0)
+    return set_error(UFAIR_ERR_ARG, "ufair_link_probe: bad arguments");
+  if (rows > 1 && ((bytes_up % rows) != 0 || (bytes_down % rows) != 0))
+    return set_error(UFAIR_ERR_ARG, "ufair_link_probe: byte counts must be multiples of rows");
+  DeviceGuard guard(device);
+  if (guard.err != cudaSuccess) return cuda_error(guard.err, "cudaSetDevice");
+  // each direction owns its own part of both buffers; pitched copies use a host pitch of twice the row
+  const size_t need = 2 * ((size_t)bytes_up + (size_t)bytes_down);
   if (g_probe.device != device || g_probe.cap < need) {
     g_probe.release();
     cudaError_t e = cudaHostAlloc(&g_probe.host, need, cudaHostAllocDefault);
@@ -393,7 +411,6 @@ extern "C" int ufair_link_probe(int device, int64_t bytes, int32_t rows, int32_t
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&g_probe.s_down, cudaStreamNonBlocking);
     if (e != cudaSuccess) {
       g_probe.release();
-      if (prev >= 0) cudaSetDevice(prev);
       return cuda_error(e, "ufair_link_probe: allocation");
     }
     memset(g_probe.host, 0, need);  // touch: the pages exist before anything is timed
@@ -401,19 +418,19 @@ extern "C" int ufair_link_probe(int device, int64_t bytes, int32_t rows, int32_t
     g_probe.device = device;
   }
   char* h_up = (char*)g_probe.host;
-  char* h_down = h_up + 2 * (size_t)bytes;
+  char* h_down = h_up + 2 * (size_t)bytes_up;
   char* d_up = (char*)g_probe.dev;
-  char* d_down = d_up + 2 * (size_t)bytes;
+  char* d_down = d_up + 2 * (size_t)bytes_up;
   auto copy = [&](bool up, cudaStream_t s) -> cudaError_t {
     if (rows > 1) {
-      const size_t w = (size_t)bytes / rows;
+      const size_t w = (size_t)(up ? bytes_up : bytes_down) / rows;
       return up ? cudaMemcpy2DAsync(d_up, w, h_up, 2 * w, w, rows, cudaMemcpyHostToDevice, s)
                 : cudaMemcpy2DAsync(h_down, 2 * w, d_down, w, w, rows, cudaMemcpyDeviceToHost, s);
     }
-    return up ? cudaMemcpyAsync(d_up, h_up, (size_t)bytes, cudaMemcpyHostToDevice, s)
-              : cudaMemcpyAsync(h_down, d_down, (size_t)bytes, cudaMemcpyDeviceToHost, s);
+    return up ? cudaMemcpyAsync(d_up, h_up, (size_t)bytes_up, cudaMemcpyHostToDevice, s)
+              : cudaMemcpyAsync(h_down, d_down, (size_t)bytes_down, cudaMemcpyDeviceToHost, s);
   };
-  const bool up = mode != 1, down = mode != 0;
+  const bool up = bytes_up > 0, down = bytes_down > 0;
   cudaError_t e = cudaSuccess;
   if (up) e = copy(true, g_probe.s_up);  // warm-up
   if (e == cudaSuccess && down) e = copy(false, g_probe.s_down);
@@ -425,18 +442,21 @@ extern "C" int ufair_link_probe(int device, int64_t bytes, int32_t rows, int32_t
     if (up) e = copy(true, g_probe.s_up);
     if (e == cudaSuccess && down) e = copy(false, g_probe.s_down);
   }
-  if (e == cudaSuccess && up) {
-    e = cudaStreamSynchronize(g_probe.s_up);
-    t_up = wall_seconds() - t0;
+  // the shorter direction is waited for first, so that each direction's own completion time is seen
+  const bool up_first = !down || (up && bytes_up <= bytes_down);
+  for (int k = 0; k < 2 && e == cudaSuccess; ++k) {
+    const bool do_up = (k == 0) == up_first;
+    if (do_up && up) {
+      e = cudaStreamSynchronize(g_probe.s_up);
+      t_up = wall_seconds() - t0;
+    } else if (!do_up && down) {
+      e = cudaStreamSynchronize(g_probe.s_down);
+      t_down = wall_seconds() - t0;
+    }
   }
-  if (e == cudaSuccess && down) {
-    e = cudaStreamSynchronize(g_probe.s_down);
-    t_down = wall_seconds() - t0;
-  }
-  if (prev >= 0) cudaSetDevice(prev);
   if (e != cudaSuccess) return cuda_error(e, "ufair_link_probe: copy");
-  const double gb = (double)bytes * reps / 1e9;
-  gbs[0] = up ? gb / t_up : 0.0;
-  gbs[1] = down ? gb / t_down : 0.0;
+  gbs[0] = up ? (double)bytes_up * reps / 1e9 / t_up : 0.0;
+  gbs[1] = down ? (double)bytes_down * reps / 1e9 / t_down : 0.0;
+  if (seconds) *seconds = t_up > t_down ? t_up : t_down;
   return UFAIR_OK;
 }

@@ -58,11 +58,19 @@
 #include "../../include/ufair.h"
 #include "ufair_math.cuh"
 
-// 1: a lane integrates all gases of its member; 0: one gas per lane.  Measured: in FP64 the two tie on
-// dense parameters (35.3 vs 35.5 ms; see the v6 note above), one gas per lane is the default; in
-// FP32, where state is half as wide, all gases per lane wins.
+// 1: a lane integrates all gases of its member; 0: one gas per lane.  Round 1 measured a tie in FP64 on
+// dense parameters (35.3 vs 35.5 ms); round 2 found why -- the logarithm's special-case branch split every
+// gas into its own basic block, so the three gases of a lane never interleaved -- and with the branch-free
+// logarithm all gases per lane wins in FP64 too (31.3 -> 28.6 ms: no idle lanes, no shuffles, one thermal
+// step per member instead of three).  Small ensembles keep one gas per lane (see UFAIR_SMALL_ENSEMBLE).
 #ifndef UFAIR_GPL_ALL_F64
-#define UFAIR_GPL_ALL_F64 0
+#define UFAIR_GPL_ALL_F64 1
+#endif
+// FP64, default alpha mode: ensembles of at most this many members run one gas per lane (3.2x as many
+// warps: a 10^4-member ensemble fills a third of the GPU's schedulers with 32-member warps, all of them
+// with 10-member warps), larger ones all gases per lane.  Both give bit-identical results.
+#ifndef UFAIR_SMALL_ENSEMBLE
+#define UFAIR_SMALL_ENSEMBLE 12288
 #endif
 #ifndef UFAIR_GPL_ALL_F32
 #define UFAIR_GPL_ALL_F32 1
@@ -108,11 +116,19 @@
 #ifndef UFAIR_MINB_F32_GPLALL
 #define UFAIR_MINB_F32_GPLALL 12
 #endif
+// ... and for the FP64 dense kernels with all gases of a member in one lane.  Measured (ms per launch at 12
+// warps/SM): [0] 29.4, [4] 29.1, [5] 28.6 (163 registers: the alpha_val and thermal constants in registers).
+#ifndef UFAIR_REGCONST_GPLALL
+#define UFAIR_REGCONST_GPLALL 5
+#endif
 #ifndef UFAIR_TT
 #define UFAIR_TT 8  // time steps per shared-memory tile (8 measured ~2 % faster than 4)
 #endif
 #ifndef UFAIR_TT_FORM  // ... for the specialised-form kernels (32 members per warp: their tiles are 3.2x as
 #define UFAIR_TT_FORM 2  // wide, and shared memory, not registers, would otherwise cap their occupancy)
+#endif
+#ifndef UFAIR_TT_GPLALL  // ... and for the dense FP64 kernels with all gases of a member in one lane
+#define UFAIR_TT_GPLALL 1  // (measured: 1 step 29.4 ms, 2 steps 29.9, 4 steps 29.3 before the constants moved to registers)
 #endif
 
 namespace ufair {
@@ -159,6 +175,10 @@ constexpr unsigned kForms4[] = {pack_form(kGasFull, kGasOneSqrt, kGasOneSqrt, kG
 // instruction stream across gases)
 constexpr int gases_per_lane(int elem_size, int n_gas, unsigned form = 0) {
   return (form != 0 || (elem_size == 8 ? UFAIR_GPL_ALL_F64 : UFAIR_GPL_ALL_F32)) ? n_gas : 1;
+}
+// the dense FP64 kernels of the default alpha mode also exist with one gas per lane, for small ensembles
+constexpr bool has_small_variant(int elem_size, int n_gas, int amode, int var) {
+  return elem_size == 8 && n_gas > 1 && UFAIR_GPL_ALL_F64 && amode == UFAIR_ALPHA_EXP && var != UFAIR_LOOP_CONC_DRIVEN;
 }
 // members per warp: rows of MW elements must be a multiple of 16 bytes for the TMA box
 constexpr int members_per_warp(int elem_size, int n_gas, int gpl) {
@@ -274,10 +294,10 @@ __host__ __device__ constexpr int compact_row(int np, int k) { return k < 4 ? k 
 template <typename Real, int NGAS, int AMODE, int GPL_, unsigned FORM = 0u> struct WarpSmem {
   static constexpr int GPL = GPL_;
   // time steps per tile: short tiles wherever an FP64 lane carries several gases (32 members per warp)
-  static constexpr int TT = (sizeof(Real) == 8 && GPL_ > 1) ? UFAIR_TT_FORM : kTT;
+  static constexpr int TT = (sizeof(Real) == 8 && GPL_ > 1) ? (FORM != 0 ? UFAIR_TT_FORM : UFAIR_TT_GPLALL) : kTT;
   // which constants live in registers (bit 0 alpha_val, bit 1 pools, bit 2 thermal): see UFAIR_REGCONST*
   static constexpr int RCM = sizeof(Real) == 4 ? ((FORM == 0 && GPL_ > 1) ? UFAIR_REGCONST_F32 : 0)
-                             : (GPL_ == 1 ? UFAIR_REGCONST : (FORM != 0 ? UFAIR_REGCONST_FORM : 0));
+                             : (GPL_ == 1 ? UFAIR_REGCONST : (FORM != 0 ? UFAIR_REGCONST_FORM : UFAIR_REGCONST_GPLALL));
   static constexpr bool HOT_SMEM = ((GPL == 1) || sizeof(Real) == 8) && !(RCM & 1);
   static constexpr int MW = members_per_warp(sizeof(Real), NGAS, GPL);
   static constexpr int G_HOT = G_COLD;                            // first hot row (if in smem)
@@ -409,7 +429,8 @@ __global__ void __launch_bounds__(kWarps * 32, min_blocks(sizeof(Real), NGAS, GP
   // for the 10^6-year pool, so the one-off prologue always runs in FP64 and rounds once)
   Real R[GPL][4], Gcum[GPL], sumR[GPL];
   Real hot[GPL][H_COUNT];  // used only when !HOT_SMEM (dead otherwise)
-  unsigned mk1[GPL], mk3[GPL];
+  unsigned mk3[GPL];
+  int nmin[GPL];  // lowest exponent alpha may take (Math::alpha_floor_exp)
   bool need_log[GPL], need_sqrt[GPL];
 #pragma unroll
   for (int gl = 0; gl < GPL; ++gl) {
@@ -425,10 +446,11 @@ __global__ void __launch_bounds__(kWarps * 32, min_blocks(sizeof(Real), NGAS, GP
     }
     const double r0 = p[UFAIR_GP_R0 * ld], rU = p[UFAIR_GP_RU * ld], rT = p[UFAIR_GP_RT * ld], rA = p[UFAIR_GP_RA * ld];
     const double C0d = p[UFAIR_GP_C0 * ld], c = p[UFAIR_GP_EMIS2CONC * ld];
-    double g1 = 0.0, sden = 0.0;
+    double g1 = 0.0, sden = 0.0, k0max = 0.0;
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
       if (q < NP) {
+        k0max = fmax(k0max, a.dt / tau[q]);
         const double z = a.h / tau[q];
         const double ez = exp(-z);
         g1 += av[q] * tau[q] * (1.0 - (1.0 + z) * ez);
@@ -453,10 +475,15 @@ __global__ void __launch_bounds__(kWarps * 32, min_blocks(sizeof(Real), NGAS, GP
       hot[gl][q] = (Real)hv[q];
       if (HOT_SMEM) SETG(gl, WS::G_HOT + q, hv[q]);
     }
-    SETG(gl, G_C0, C0d);
-    SETG(gl, G_INVC0, 1.0 / C0d);
-    SETG(gl, G_SQRTC0, sqrt(C0d));
+    nmin[gl] = M::alpha_floor_exp(k0max, AMODE == UFAIR_ALPHA_NEWTON ? 8 : 0);
+    pin(reinterpret_cast<uint32_t&>(nmin[gl]));
     const Real f1v = p[UFAIR_GP_F1 * ld], f3v = p[UFAIR_GP_F3 * ld];
+    SETG(gl, G_C0, C0d);
+    // the logarithm's argument is 1 + sumR / C0; a gas WITHOUT the log term (f1 == 0) gets 1 / C0 := 0 here,
+    // so its argument is exactly 1, its logarithm exactly 0 and the term exactly zero -- also for C0 = 0
+    // gases, where 1 / C0 is infinite -- with no mask or test in the loop
+    SETG(gl, G_INVC0, f1v != Real(0) ? 1.0 / C0d : 0.0);
+    SETG(gl, G_SQRTC0, sqrt(C0d));
     SETG(gl, G_F1, f1v);
     SETG(gl, G_F2, p[UFAIR_GP_F2 * ld]);
     SETG(gl, G_F3, f3v);
@@ -471,9 +498,7 @@ __global__ void __launch_bounds__(kWarps * 32, min_blocks(sizeof(Real), NGAS, GP
     // (PLAIN: no vote, no branch in the loop -- the masks below still zero an absent term)
     need_log[gl] = (TERMS & UFAIR_TERM_LOG) && (PLAIN || __any_sync(FULL, f1v != Real(0)));
     need_sqrt[gl] = (TERMS & UFAIR_TERM_SQRT) && (PLAIN || __any_sync(FULL, f3v != Real(0)));
-    mk1[gl] = (f1v != Real(0)) ? 0xffffffffu : 0u;
     mk3[gl] = (f3v != Real(0)) ? 0xffffffffu : 0u;
-    pin(mk1[gl]);
     pin(mk3[gl]);
     const Real* si = a.state_in;
 #pragma unroll
@@ -559,7 +584,8 @@ __global__ void __launch_bounds__(kWarps * 32, min_blocks(sizeof(Real), NGAS, GP
         fx_next = __ldg(fx_scen_p + (long long)min(t + 1, n_t - 1) * a.n_scen);
       }
     }
-    Real Fsum = 0;
+    Real Fg[GPL];
+    bool bad = false;  // some logarithm of this step has an argument outside the fast path's domain
 #pragma unroll
     for (int gl = 0; gl < GPL; ++gl) {
       const int NP = form_pools(FORM, gl);
@@ -586,11 +612,16 @@ __global__ void __launch_bounds__(kWarps * 32, min_blocks(sizeof(Real), NGAS, GP
           const Real umax = HOT_SMEM ? PARG(gl, WS::G_HOT + H_UMAX) : hot[gl][H_UMAX];
           u = (u > umax) ? umax : u;
         }
-        alpha = (AMODE == UFAIR_ALPHA_SINH) ? PARG(gl, WS::G_X0) * M::sinh_pair(u, tb) : M::exp_(u, tb);
+        alpha = (AMODE == UFAIR_ALPHA_SINH) ? PARG(gl, WS::G_X0) * M::sinh_pair(u, tb, nmin[gl]) : M::exp_(u, tb, nmin[gl]);
         if (AMODE == UFAIR_ALPHA_NEWTON) {
           const Real iirf = (u - PARG(gl, WS::G_X0 + 1)) * PARG(gl, WS::G_X0);
           const Real invc = PARG(gl, WS::G_X0 + 2);
+#ifdef UFAIR_EXP_NEWTON_K  // experiment: what a compile-time (unrolled) iteration count is worth over the run-time loop
+#pragma unroll
+          for (int it = 0; it < UFAIR_EXP_NEWTON_K; ++it) {
+#else
           for (int it = 0; it < a.newton_iters; ++it) {
+#endif
             const Real ia = M::rcp(alpha);
             Real f = -iirf, fp = 0;
 #pragma unroll
@@ -633,17 +664,44 @@ __global__ void __launch_bounds__(kWarps * 32, min_blocks(sizeof(Real), NGAS, GP
       Gcum[gl] = fma(e, dt, Gcum[gl]);
       sumR[gl] = sum_pools(R[gl], NP);
       const Real C = PARG(gl, G_C0) + sumR[gl];
-      // ---- step_forc
-      // (the log / sqrt VALUE is masked, not the product, so that a zero coefficient with an
-      // infinite or NaN function value -- C0 = 0 gases -- still contributes exactly zero)
+      // ---- step_forc: F = f2 (C - C0) + f1 ln(C / C0) + f3 (sqrt C - sqrt C0), with C - C0 = sumR and
+      // C / C0 = 1 + sumR / C0.  The logarithm runs its branch-free fast path for every gas of the lane
+      // first (one basic block: the gases interleave); arguments outside its domain are patched after
+      // the gas loop.  The sqrt VALUE is masked, not the product, so that a zero coefficient with a NaN
+      // function value still contributes exactly zero.
       Real F = (TERMS & UFAIR_TERM_LIN) ? PARG(gl, G_F2) * sumR[gl] : Real(0);
-      if (need_log[gl]) F = fma(PARG(gl, G_F1), M::mask(M::log_(C * PARG(gl, G_INVC0)), mk1[gl]), F);
+      if (need_log[gl]) {
+        const Real y = fma(sumR[gl], PARG(gl, G_INVC0), Real(1));
+        F = fma(PARG(gl, G_F1), M::log_fast(y), F);
+        bad = bad || M::not_normal(y);
+      }
       if (need_sqrt[gl]) F = fma(PARG(gl, G_F3), M::mask(M::sqrt_(C) - PARG(gl, G_SQRTC0), mk3[gl]), F);
+      Fg[gl] = F;
       // (PLAIN: the lane predicates themselves, not bits re-tested every step)
       if (ALLOUT ? active : PLAIN ? st_c : (wm & UFAIR_OUT_C) != 0) st_stream(pC + gl * gstride, C);
-      if (ALLOUT ? active : PLAIN ? st_rf : (wm & UFAIR_OUT_RF) != 0) st_stream(pRF + gl * gstride, F);
       if (!PLAIN && (wm & UFAIR_OUT_ALPHA)) st_stream(pC + dA + gl * gstride, alpha);
-      Fsum = (gl == 0) ? F : Fsum + F;
+    }
+    if (__builtin_expect(bad, 0)) {  // never on a physical trajectory: redo those gases' forcing with the special values
+#pragma unroll
+      for (int gl = 0; gl < GPL; ++gl) {
+        const unsigned TERMS = form_terms(FORM, gl);
+        if (need_log[gl]) {
+          const Real y = fma(sumR[gl], PARG(gl, G_INVC0), Real(1));
+          if (M::not_normal(y)) {
+            Real F = (TERMS & UFAIR_TERM_LIN) ? PARG(gl, G_F2) * sumR[gl] : Real(0);
+            F = fma(PARG(gl, G_F1), M::log_special(y), F);
+            if (need_sqrt[gl])
+              F = fma(PARG(gl, G_F3), M::mask(M::sqrt_(PARG(gl, G_C0) + sumR[gl]) - PARG(gl, G_SQRTC0), mk3[gl]), F);
+            Fg[gl] = F;
+          }
+        }
+      }
+    }
+    Real Fsum = 0;
+#pragma unroll
+    for (int gl = 0; gl < GPL; ++gl) {
+      if (ALLOUT ? active : PLAIN ? st_rf : (wm & UFAIR_OUT_RF) != 0) st_stream(pRF + gl * gstride, Fg[gl]);
+      Fsum = (gl == 0) ? Fg[gl] : Fsum + Fg[gl];
     }
     pC += ld;
     pRF += ld;
@@ -668,10 +726,6 @@ __global__ void __launch_bounds__(kWarps * 32, min_blocks(sizeof(Real), NGAS, GP
     Tprev = T;
     if (ALLOUT ? owner : PLAIN ? st_t : (wm & UFAIR_OUT_T) != 0) st_stream(pT, T);
     pT += ld;
-#if defined(UFAIR_EXP_PAD) || defined(UFAIR_EXP_PAD64) || defined(UFAIR_EXP_PADUR) || defined(UFAIR_EXP_PADUR4) || \
-    defined(UFAIR_EXP_PADRRU) || defined(UFAIR_EXP_PADR3)
-#include "ufair_kernel_pads.inc"  // cost-model experiments; never in the shipped build
-#endif
   };
 
   // ---------------- the time loop --------------------------------------------------------------------
@@ -780,6 +834,19 @@ inline unsigned pick_form(const ufair_desc* d) {
   return 0;
 }
 
+// dense kernels: all gases per lane, or -- small FP64 ensembles in the default alpha mode -- one gas per lane
+template <typename Real, int NGAS, int AMODE, int VAR> int launch_dense(const ufair_desc* d, const KArgs<Real>& a, cudaStream_t stream) {
+  if constexpr (has_small_variant(sizeof(Real), NGAS, AMODE, VAR)) {
+    if (d->n_member <= UFAIR_SMALL_ENSEMBLE) return launch_variant<Real, NGAS, AMODE, 1, 0u, VAR>(d, a, stream);
+  }
+  return launch_variant<Real, NGAS, AMODE, gases_per_lane(sizeof(Real), NGAS), 0u, VAR>(d, a, stream);
+}
+// the lane mapping launch_integrate picks for this descriptor (ufair_kernel_variant reports it)
+inline int runtime_gases_per_lane(const ufair_desc* d, int elem_size, unsigned form, int var) {
+  if (form == 0 && has_small_variant(elem_size, d->n_gas, d->alpha_mode, var) && d->n_member <= UFAIR_SMALL_ENSEMBLE) return 1;
+  return gases_per_lane(elem_size, d->n_gas, form);
+}
+
 // dense launcher, and the specialised forms of the EXP alpha mode when the descriptor's gas_form allows
 #define UFAIR_TRY_FORM(Real, NGAS, F)                                                                  \
   if (form == F) {                                                                                     \
@@ -795,25 +862,19 @@ inline unsigned pick_form(const ufair_desc* d) {
     const unsigned form = pick_form(d);                                                                \
     const int var = plain_variant(d);                                                                  \
     TRY_FORMS                                                                                          \
-    if (wants_inverse(d))                                                                              \
-      return launch_variant<Real, NGAS, UFAIR_ALPHA_EXP, gases_per_lane(sizeof(Real), NGAS), 0u, kVarInverse>(d, a, stream); \
-    if (var == kVarPlain)                                                                              \
-      return launch_variant<Real, NGAS, UFAIR_ALPHA_EXP, gases_per_lane(sizeof(Real), NGAS), 0u, kVarPlain>(d, a, stream); \
-    if (var == kVarPlainFx)                                                                            \
-      return launch_variant<Real, NGAS, UFAIR_ALPHA_EXP, gases_per_lane(sizeof(Real), NGAS), 0u, kVarPlainFx>(d, a, stream); \
-    if (var == kVarPlainSub)                                                                           \
-      return launch_variant<Real, NGAS, UFAIR_ALPHA_EXP, gases_per_lane(sizeof(Real), NGAS), 0u, kVarPlainSub>(d, a, stream); \
-    return launch_variant<Real, NGAS, UFAIR_ALPHA_EXP, gases_per_lane(sizeof(Real), NGAS), 0u>(d, a, stream); \
+    if (wants_inverse(d)) return launch_dense<Real, NGAS, UFAIR_ALPHA_EXP, kVarInverse>(d, a, stream);    \
+    if (var == kVarPlain) return launch_dense<Real, NGAS, UFAIR_ALPHA_EXP, kVarPlain>(d, a, stream);       \
+    if (var == kVarPlainFx) return launch_dense<Real, NGAS, UFAIR_ALPHA_EXP, kVarPlainFx>(d, a, stream);   \
+    if (var == kVarPlainSub) return launch_dense<Real, NGAS, UFAIR_ALPHA_EXP, kVarPlainSub>(d, a, stream); \
+    return launch_dense<Real, NGAS, UFAIR_ALPHA_EXP, kVarGeneral>(d, a, stream);                           \
   }
 
 #define UFAIR_DEFINE_LAUNCH(Real, NGAS, AMODE)                                                         \
   template <> int launch_integrate<Real, NGAS, AMODE>(const ufair_desc* d, const KArgs<Real>& a,       \
                                                       cudaStream_t stream) {                           \
-    if (wants_inverse(d))                                                                              \
-      return launch_variant<Real, NGAS, AMODE, gases_per_lane(sizeof(Real), NGAS), 0u, kVarInverse>(d, a, stream); \
-    if (plain_variant(d) == kVarPlain)                                                                 \
-      return launch_variant<Real, NGAS, AMODE, gases_per_lane(sizeof(Real), NGAS), 0u, kVarPlain>(d, a, stream); \
-    return launch_variant<Real, NGAS, AMODE, gases_per_lane(sizeof(Real), NGAS), 0u>(d, a, stream);    \
+    if (wants_inverse(d)) return launch_dense<Real, NGAS, AMODE, kVarInverse>(d, a, stream);            \
+    if (plain_variant(d) == kVarPlain) return launch_dense<Real, NGAS, AMODE, kVarPlain>(d, a, stream); \
+    return launch_dense<Real, NGAS, AMODE, kVarGeneral>(d, a, stream);                                  \
   }
 
 }  // namespace ufair

@@ -20,23 +20,19 @@
 #include <math.h>
 #include <stdint.h>
 
-// 1: table-driven exponentials (32-entry 2^(-j/32) table per warp in shared memory, degree-4
-// polynomial: 11 FP64 operations per exponential instead of 17).  Measured on B200:
-// FP64 instructions per warp-step 147 -> 122, but every exponential gains a bank-conflicted LDS.128
-// and ~10 integer / select instructions on its dependent chain, and the LSU wavefront pipe (63 % busy
-// before) becomes the limiter: 38.2 -> 38.8 ms dense, 25.4 -> 29.2 ms on the specialised forms.
-// Kept (parity-green, tests/test_gpu_math.py passes with it) as a measured alternative; default off.
-#ifndef UFAIR_EXP_TABLE
-#define UFAIR_EXP_TABLE 0
-#endif
 // 1: FP32 exponentials on MUFU.EX2 (0: range reduction + polynomial on the FMA pipe)
 #ifndef UFAIR_F32_MUFU
 #define UFAIR_F32_MUFU 1
 #endif
+// 1: sqrt(0) = 0 through an integer clamp of the MUFU.RSQ64H seed (one instruction) instead of a test on
+// the argument and two selects (four)
+#ifndef UFAIR_SQRT_SEED_CLAMP
+#define UFAIR_SQRT_SEED_CLAMP 1
+#endif
 
 namespace ufair {
 
-constexpr unsigned kExpTableBytes = UFAIR_EXP_TABLE ? 512u : 0u;  // per warp, FP64 kernels only
+constexpr unsigned kExpTableBytes = 0u;  // (a table-driven exponential was measured and dropped: DESIGN.md 4.1)
 
 // expm1(r) = r + r^2 Q(r), |r| <= ln2/2; Q[0] + Q[1] r + ... + Q[9] r^9
 static __constant__ double cExpQ[10] = {
@@ -49,48 +45,6 @@ static __constant__ double cLogL[7] = {0x1.5555555555558p-1, 0x1.99999999952e2p-
 // log2(e), -ln2_hi, -ln2_lo, magic (2^52+2^51), ln2_hi, ln2_lo, 2^52+2^31
 static __constant__ double cK[7] = {0x1.71547652b82fep+0, -0x1.62e42fefa39efp-1, -0x1.abc9e3b39803fp-56, 0x1.8p52,
                                     0x1.62e42fefa39efp-1,  0x1.abc9e3b39803fp-56, 0x1.0000080000000p52};
-// Table-driven exponentials (UFAIR_EXP_TABLE=1): x = (32 n + j) ln2/32 + r with
-// |r| <= ln2/64, e^-x = 2^-n T_j e^-r... (see Math<double>::decay).  Pairs (T_j, U_j) =
-// (2^(-j/32), 1 - 2^(-j/32)), both correctly rounded; copied to shared memory by each warp, because
-// a lane-dependent index into __constant__ memory would serialise.
-static __constant__ double cExpT[64] = {
-    0x1.0000000000000p+0, 0x0.0p+0,
-    0x1.f50765b6e4540p-1, 0x1.5f134923757f3p-6,
-    0x1.ea4afa2a490dap-1, 0x1.5b505d5b6f268p-5,
-    0x1.dfc97337b9b5fp-1, 0x1.01b466423250ap-4,
-    0x1.d5818dcfba487p-1, 0x1.53f391822dbc7p-4,
-    0x1.cb720dcef9069p-1, 0x1.a46f918837cb7p-4,
-    0x1.c199bdd85529cp-1, 0x1.f332113d56b1fp-4,
-    0x1.b7f76f2fb5e47p-1, 0x1.20224341286e4p-3,
-    0x1.ae89f995ad3adp-1, 0x1.45d819a94b14bp-3,
-    0x1.a5503b23e255dp-1, 0x1.6abf137076a8ep-3,
-    0x1.9c49182a3f090p-1, 0x1.8edb9f5703dc0p-3,
-    0x1.93737b0cdc5e5p-1, 0x1.b23213cc8e86cp-3,
-    0x1.8ace5422aa0dbp-1, 0x1.d4c6af7557c93p-3,
-    0x1.82589994cce13p-1, 0x1.f69d99accc7b6p-3,
-    0x1.7a11473eb0187p-1, 0x1.0bdd71829fcf2p-2,
-    0x1.71f75e8ec5f74p-1, 0x1.1c1142e274118p-2,
-    0x1.6a09e667f3bcdp-1, 0x1.2bec333018867p-2,
-    0x1.6247eb03a5585p-1, 0x1.3b7029f8b54f7p-2,
-    0x1.5ab07dd485429p-1, 0x1.4a9f0456f57adp-2,
-    0x1.5342b569d4f82p-1, 0x1.597a952c560fcp-2,
-    0x1.4bfdad5362a27p-1, 0x1.6804a5593abb2p-2,
-    0x1.44e086061892dp-1, 0x1.763ef3f3ceda6p-2,
-    0x1.3dea64c123422p-1, 0x1.842b367db97bcp-2,
-    0x1.371a7373aa9cbp-1, 0x1.91cb1918aac6bp-2,
-    0x1.306fe0a31b715p-1, 0x1.9f203eb9c91d6p-2,
-    0x1.29e9df51fdee1p-1, 0x1.ac2c415c0423ep-2,
-    0x1.2387a6e756238p-1, 0x1.b8f0b23153b8fp-2,
-    0x1.1d4873168b9aap-1, 0x1.c56f19d2e8cabp-2,
-    0x1.172b83c7d517bp-1, 0x1.d1a8f87055d0ap-2,
-    0x1.11301d0125b51p-1, 0x1.dd9fc5fdb495fp-2,
-    0x1.0b5586cf9890fp-1, 0x1.e954f260cede1p-2,
-    0x1.059b0d3158574p-1, 0x1.f4c9e59d4f518p-2};
-// expm1(r) = r + r^2 (1/2 + r Q4(r)), |r| <= ln2/64: max rel err 2.0e-17 (tools/gen_poly.py)
-static __constant__ double cExpQ4[4] = {0x1.555555554dd45p-3, 0x1.555555555194dp-5, 0x1.11114f8a7941cp-7,
-                                        0x1.6c16ffe57d9c9p-10};
-// 32 log2(e), ln2/32 high and low parts
-static __constant__ double cK32[3] = {0x1.71547652b82fep+5, 0x1.62e42fefa39efp-6, 0x1.abc9e3b39803fp-61};
 static __constant__ float cExpQf[5] = {5.000000000e-01f, 1.666657776e-01f, 4.166655615e-02f, 8.363173343e-03f,
                                        1.392617589e-03f};
 
@@ -128,72 +82,12 @@ template <> struct Math<double> {
     return fma(nd, cK[2], r);
   }
 
-#if UFAIR_EXP_TABLE
-  // expm1(r) for |r| <= ln2/64: r + r^2 (1/2 + r Q4(r)); the 1/2 is an immediate operand
-  static __device__ __forceinline__ double expm1_small(double r) {
-    double q = cExpQ4[3];
-    q = fma(q, r, cExpQ4[2]);
-    q = fma(q, r, cExpQ4[1]);
-    q = fma(q, r, cExpQ4[0]);
-    q = fma(q, r, 0.5);
-    return fma(r * r, q, r);
-  }
-  static __device__ __forceinline__ void lds_pair(uint32_t a, double& t, double& u) {
-    asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(t), "=d"(u) : "r"(a));
-  }
-  static __device__ __forceinline__ double lds_one(uint32_t a) {
-    double t;
-    asm volatile("ld.shared.f64 %0, [%1];" : "=d"(t) : "r"(a));
-    return t;
-  }
-  // each warp's copy of cExpT in shared memory (tb = its 32-bit shared address); lane j fills entry j
-  static __device__ __forceinline__ void fill_table(uint32_t tb, int lane) {
-    asm volatile("st.shared.v2.f64 [%0], {%1, %2};" ::"r"(tb + 16u * (uint32_t)lane), "d"(cExpT[2 * lane]),
-                 "d"(cExpT[2 * lane + 1])
-                 : "memory");
-  }
-
-  // m = 1 - exp(-x), x >= 0 (NaN, +inf -> NaN).  k = rint(32 x / ln2) = 32 n + j, r = k ln2/32 - x:
-  //   exp(-x) = 2^-n T_j e^r,   m = (1 - 2^-n T_j) - 2^-n T_j expm1(r).
-  // For n = 0 the first term is the tabulated U_j = 1 - T_j (correctly rounded: no cancellation error
-  // from T_j's own rounding, so tiny x keep ~1 ulp); for n >= 1 it is a plain subtraction (m >= 1/2).
-  // 2^-n is applied in the integer domain and clamped at 2^-1000; x >= 4.6e7, where k no longer fits
-  // the low word of the magic-number sum, saturates the same way (m = 1).  11 FP64 operations.
-  static __device__ __forceinline__ double decay(double x, uint32_t tb) {
-    const double t = fma(x, cK32[0], kMagic);
-    int k = __double2loint(t);
-    double r = fma(t - kMagic, cK32[1], -x);
-    const bool big = (unsigned)(__double2hiint(t) - 0x43380001) < 0x3cb7ffffu;  // finite, k >= 2^32
-    k = big ? 32000 : k;
-    r = __hiloint2double(big ? 0 : __double2hiint(r), big ? 0 : __double2loint(r));
-    const int n = min(k >> 5, 1000);
-    double T, U;
-    lds_pair(tb + 16u * (uint32_t)(k & 31), T, U);
-    const double sT = __hiloint2double(__double2hiint(T) - (n << 20), __double2loint(T));
-    const double p = expm1_small(r);
-    const double d = 1.0 - sT;
-    const double X = __hiloint2double(n == 0 ? __double2hiint(U) : __double2hiint(d),
-                                      n == 0 ? __double2loint(U) : __double2loint(d));
-    return fma(-sT, p, X);
-  }
-
-  // exp(u), saturating at 2^+-40 (alpha is kept inside [9e-13, 1.1e12]); |u| < 4.6e7, NaN/inf -> NaN.
-  // k = rint(-32 u / ln2) = 32 n + j (floor division), r = u + k ln2/32: exp(u) = 2^-n T_j (1 + expm1(r)).
-  static __device__ __forceinline__ double exp_(double u, uint32_t tb) {
-    const double t = fma(-u, cK32[0], kMagic);
-    const int k = __double2loint(t);
-    const double kd = t - kMagic;
-    double r = fma(kd, cK32[1], u);
-    r = fma(kd, cK32[2], r);
-    const int n = max(min(k >> 5, 40), -40);
-    const double T = lds_one(tb + 16u * (uint32_t)(k & 31));
-    const double sT = __hiloint2double(__double2hiint(T) - (n << 20), __double2loint(T));
-    return fma(sT, expm1_small(r), sT);
-  }
-#else
   static __device__ __forceinline__ void fill_table(uint32_t, int) {}
-  // m = 1 - exp(-x) for 0 <= x <= 1e15 (larger x, inf: NaN; NaN propagates).  2^n is clamped at
-  // 2^-1000 in the integer domain, so the result saturates at exactly 1 without an FP64 compare.
+  // m = 1 - exp(-x) for 0 <= x < 1.4e9 (NaN propagates).  2^n is clamped at 2^-1000 in the integer
+  // domain, so the result saturates at exactly 1 without an FP64 compare.  n is the LOW word of the
+  // magic-number sum, so it aliases once x log2(e) reaches 2^31 (x ~ 1.49e9); the integrator never gets
+  // there: x = (dt / tau_i) / alpha, and alpha's lower saturation is raised per lane (alpha_floor_exp
+  // below) so that max_i(dt / tau_i) / alpha stays below 7.6e8.
   static __device__ __forceinline__ double decay(double x, uint32_t) {
     // single-constant reduction: ln2's low word shifts r by n * 2.3e-17, i.e. the result by
     // <= 2^n * |n| * 2.3e-17 absolute -- below half an ulp of m for every n <= -1 (m >= 0.29)
@@ -206,15 +100,23 @@ template <> struct Math<double> {
     return fma(-s, p, 1.0 - s);                         // 1 - s(1 + p); 1 - s is exact for n <= 0
   }
 
-  // exp(u), saturating at 2^+-40 (alpha is kept inside [9e-13, 1.1e12]); NaN/inf -> NaN.
-  static __device__ __forceinline__ double exp_(double u, uint32_t) {
+  // exp(u), saturating at 2^40 above and at 2^nmin below (nmin >= -40: alpha is kept inside
+  // [9e-13, 1.1e12], or a narrower range whose lower end keeps decay()'s argument in its domain);
+  // NaN/inf -> NaN.
+  static __device__ __forceinline__ double exp_(double u, uint32_t, int nmin = -40) {
     int n;
     double r = reduce(u, n);
     double v = 1.0 + expm1_reduced(r);
-    n = max(min(n, 40), -40);
+    n = max(min(n, 40), nmin);
     return __hiloint2double(__double2hiint(v) + (n << 20), __double2loint(v));
   }
-#endif
+  // the lowest exponent alpha may take for a lane whose fastest pool has dt / tau = k0max: with
+  // alpha >= 2^nmin / sqrt(2), x = k0max / alpha <= k0max 2^(-nmin) sqrt(2) < 2^28 2 sqrt(2) = 7.6e8.
+  // `slack` lowers alpha's reach below the seed (Newton mode halves alpha at most once per iteration).
+  static __device__ __forceinline__ int alpha_floor_exp(double k0max, int slack) {
+    const int e = ((__double2hiint(k0max) >> 20) & 0x7ff) - 1023;  // ilogb for positive normal k0max
+    return min(40, max(-40, e - 28 + slack));
+  }
 
   // 1/a for positive normal a: MUFU.RCP64H seed y (relative error e ~ 2^-20) and one third-order
   // step y (1 + e + e^2), error e^3: 3 DFMA, ~1 ulp.
@@ -226,28 +128,35 @@ template <> struct Math<double> {
   }
 
   // sqrt(a) for a >= 0: MUFU.RSQ64H seed y, t = a y, e = 1 - t y, sqrt = t (1 + e/2 + 3 e^2 / 8),
-  // error 5 e^3 / 16: 5 FP64 ops.  sqrt(0) = 0 (integer test, no FP64 compare); a < 0 -> NaN.
+  // error 5 e^3 / 16: 5 FP64 ops.  sqrt(0) = 0 (integer clamp of the seed, no FP64 compare); a < 0 -> non-finite
+  // (-inf with the seed clamp, NaN without: either way the member's next step is NaN).
   static __device__ __forceinline__ double sqrt_(double a) {
     double y;
     asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(a));
+#if UFAIR_SQRT_SEED_CLAMP
+    // a = 0: the seed is +inf and a y would be NaN; clamping the seed's high word to the largest finite
+    // value (one integer min) gives t = 0 and sqrt(0) = 0 without a test on a and two selects (measured:
+    // 29.8 -> 29.4 ms).  The NaN seed of a negative argument is clamped too, so sqrt(a < 0) = -inf.
+    y = __hiloint2double(min(__double2hiint(y), 0x7fe00000), 0);
+#endif
     double t = a * y;
     double e = fma(-t, y, 1.0);
     double p = fma(e, 0.375, 0.5) * e;
     double g = fma(t, p, t);
+#if UFAIR_SQRT_SEED_CLAMP
+    return g;
+#else
     return ((__double2hiint(a) << 1) | __double2loint(a)) == 0 ? 0.0 : g;
+#endif
   }
 
-  // log(y).  Positive normal y on the fast path; everything else takes the (never hot) libm call.
-  static __device__ __forceinline__ double log_(double y) {
+  // log(y) for a positive normal y: 2 atanh-series with a reciprocal instead of a division.  Branch-free on
+  // purpose: a special-case branch per logarithm splits the time step into basic blocks and stops the
+  // compiler from interleaving the independent gases of a lane (measured: 33.1 -> 29.6 ms on the dense
+  // all-gases-per-lane kernel).  `not_normal(y)` says whether y is outside the fast path's domain; callers
+  // test it once per step for all their logarithms and patch the rare cases with log_special().
+  static __device__ __forceinline__ double log_fast(double y) {
     int hi = __double2hiint(y), lo = __double2loint(y);
-    // not a positive normal number (never on a physical trajectory): -inf for +-0 and subnormals
-    // (flushed), NaN for negatives, y itself for +inf / NaN.  Kept tiny so it stays predicated.
-#ifndef UFAIR_EXP_LOG_NOSPECIAL  // experiment: what the special-case branch costs (basic-block splitting)
-    if (__builtin_expect((unsigned)(hi - 0x00100000) >= 0x7fe00000u, 0))
-#else
-    if (false)
-#endif
-      return (unsigned)(hi & 0x7fffffff) < 0x00100000u ? -INFINITY : (hi < 0 ? __longlong_as_double(0x7ff8000000000000ll) : y);
     // y = 2^e m with m in [sqrt(1/2), sqrt(2)): bias the high word so the exponent field rolls over
     // exactly at the mantissa of sqrt(2) (0x6a09e...), the fdlibm normalisation -- 4 integer ops
     const int hx = hi + (0x3ff00000 - 0x3fe6a09e);
@@ -270,6 +179,19 @@ template <> struct Math<double> {
     t = fma(2.0, s, t);
     return fma(ed, cK[4], t);
   }
+  // not a positive normal number (never on a physical trajectory)
+  static __device__ __forceinline__ bool not_normal(double y) {
+    return (unsigned)(__double2hiint(y) - 0x00100000) >= 0x7fe00000u;
+  }
+  // ... and what the logarithm is there: -inf for +-0 and subnormals (flushed), NaN for negatives, y itself
+  // for +inf / NaN
+  static __device__ __forceinline__ double log_special(double y) {
+    const int hi = __double2hiint(y);
+    return (unsigned)(hi & 0x7fffffff) < 0x00100000u ? -INFINITY : (hi < 0 ? __longlong_as_double(0x7ff8000000000000ll) : y);
+  }
+  static __device__ __forceinline__ double log_(double y) {  // any y (probe, one-off uses)
+    return __builtin_expect(not_normal(y), 0) ? log_special(y) : log_fast(y);
+  }
 
   static __device__ __forceinline__ double fmax_(double a, double b) { return fmax(a, b); }
   static __device__ __forceinline__ int floor_to_int(double a) { return __double2int_rd(a); }  // saturating
@@ -282,8 +204,8 @@ template <> struct Math<double> {
   static __device__ __forceinline__ double mask(double v, unsigned m) {
     return __hiloint2double(__double2hiint(v) & (int)m, __double2loint(v) & (int)m);
   }
-  static __device__ __forceinline__ double sinh_pair(double v, uint32_t tb) {  // sinh via exp and 1/exp
-    double e = exp_(v, tb);
+  static __device__ __forceinline__ double sinh_pair(double v, uint32_t tb, int nmin = -40) {  // sinh via exp and 1/exp
+    double e = exp_(v, tb, nmin);
     return 0.5 * (e - rcp(e));
   }
 };
@@ -334,7 +256,7 @@ template <> struct Math<float> {
   }
   // exp(u) = 2^n ex2(f), n = rint(u log2 e) clamped to +-40, f = u log2 e - n in two FMAs (so the
   // argument rounding does not grow with |u|): 7 instructions instead of 16
-  static __device__ __forceinline__ float exp_(float u, uint32_t = 0) {
+  static __device__ __forceinline__ float exp_(float u, uint32_t = 0, int = -40) {
     const float t = fmaf(u, kLog2e, kMagic);
     int n = __float_as_int(t) - 0x4b400000;
     const float nd = t - kMagic;
@@ -352,7 +274,7 @@ template <> struct Math<float> {
     float s = __int_as_float((127 + n) << 23);
     return fmaf(-s, p, 1.0f - s);
   }
-  static __device__ __forceinline__ float exp_(float u, uint32_t = 0) {
+  static __device__ __forceinline__ float exp_(float u, uint32_t = 0, int = -40) {
     int n;
     float r = reduce(u, n);
     float v = 1.0f + expm1_reduced(r);
@@ -375,13 +297,18 @@ template <> struct Math<float> {
     asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(l) : "f"(y));
     return l * 0.6931471805599453f;
   }
+  // MUFU.LG2 handles every argument itself: the FP32 kernels never need the patch-up path
+  static __device__ __forceinline__ float log_fast(float y) { return log_(y); }
+  static __device__ __forceinline__ bool not_normal(float) { return false; }
+  static __device__ __forceinline__ float log_special(float y) { return log_(y); }
   static __device__ __forceinline__ float fmax_(float a, float b) { return fmaxf(a, b); }
   static __device__ __forceinline__ int floor_to_int(float a) { return __float2int_rd(a); }
   static __device__ __forceinline__ float bin_x(float T, float lo, float invw) {
     return __fmul_rn(__fsub_rn(T, lo), invw);
   }
   static __device__ __forceinline__ float mask(float v, unsigned m) { return __int_as_float(__float_as_int(v) & (int)m); }
-  static __device__ __forceinline__ float sinh_pair(float v, uint32_t = 0) {
+  static __device__ __forceinline__ int alpha_floor_exp(double, int) { return -40; }  // FP32 decay() saturates by itself
+  static __device__ __forceinline__ float sinh_pair(float v, uint32_t = 0, int = -40) {
     float e = exp_(v);
     return 0.5f * (e - rcp(e));
   }

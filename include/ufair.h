@@ -218,6 +218,15 @@ int ufair_stats_pass_f32(const ufair_desc* d, void* stream);
  * moments[hist_rows][UFAIR_MOM_COUNT] (sum, sumsq, min, max as doubles). */
 int ufair_stats_finalize(const ufair_desc* d, uint64_t* hist, double* moments, void* stream);
 
+/* The same fold in the layout the cross-GPU reduction uses -- two buffers, two collectives:
+ *   sums[hist_rows][hist_bins + 2]: the counts as doubles (integers below 2^53 add exactly in any order,
+ *     so the reduced histogram is bitwise independent of the GPU count), then sum T and sum T^2 -> all-reduce SUM
+ *   ext[hist_rows][2]: max T, -min T                                                            -> all-reduce MAX
+ * and back: ufair_stats_unpack() turns the reduced buffers into hist (uint64) and moments. */
+int ufair_stats_finalize_packed(const ufair_desc* d, double* sums, double* ext, void* stream);
+int ufair_stats_unpack(const double* sums, const double* ext, int32_t rows, int32_t bins, uint64_t* hist,
+                       double* moments, void* stream);
+
 /* Percentiles read off the (reduced) per-step histogram CDF, linear inside the bin:
  * out[row][j] = percentile pcts[j] (0..100) of row `row`; hist: [rows][bins] counts, pcts: [n_pct]
  * (device), out: [rows][n_pct] (device).  Bit-identical to the oracle's percentiles_from_hist. */
@@ -287,13 +296,15 @@ int ufair_run_host_f64(ufair_workspace* ws, const ufair_desc* d, uint64_t* hist,
 int ufair_run_host_f32(ufair_workspace* ws, const ufair_desc* d, uint64_t* hist, double* moments);
 
 /* ---- host-link probe (measurement support: the ceiling bench.py states e2e against) ----
- * Times `reps` copies of `bytes` bytes between a page-locked host buffer (allocated and kept by the
- * probe) and device memory on `device`.  mode 0: host -> device; 1: device -> host; 2: both at once on
- * two streams.  rows <= 1: contiguous cudaMemcpyAsync; rows > 1: one pitched cudaMemcpy2DAsync of `rows`
- * rows per copy (host pitch = twice the row width: the shape of a member-chunk copy).  Wall clock from the
- * first enqueue to the stream's completion.  gbs[0] = host -> device GB/s, gbs[1] = device -> host GB/s
- * (0 for a direction the mode does not use).  bytes <= 0 releases the probe's buffers. */
-int ufair_link_probe(int device, int64_t bytes, int32_t rows, int32_t reps, int32_t mode, double* gbs);
+ * Times `reps` rounds of copies between a page-locked host buffer (allocated and kept by the probe) and
+ * device memory on `device`: bytes_up bytes host -> device and bytes_down bytes device -> host per round,
+ * the two directions at once on two streams (either may be 0: that direction alone).  rows <= 1:
+ * contiguous cudaMemcpyAsync; rows > 1: one pitched cudaMemcpy2DAsync of `rows` rows per copy (host pitch =
+ * twice the row width: the shape of a member-chunk copy).  Wall clock from the first enqueue to each
+ * stream's completion: gbs[0] = host -> device GB/s, gbs[1] = device -> host GB/s, *seconds (may be NULL)
+ * = until both are done.  bytes_up <= 0 and bytes_down <= 0 releases the probe's buffers. */
+int ufair_link_probe(int device, int64_t bytes_up, int64_t bytes_down, int32_t rows, int32_t reps, double* gbs,
+                     double* seconds);
 
 /* ---- device-math probe (test support): y[i] = op(x[i]) with the kernel's own math routines.
  * op: 0 decay(x)=1-exp(-x), 1 exp, 2 rcp, 3 sqrt, 4 log, 5 sinh. */

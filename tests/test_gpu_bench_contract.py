@@ -13,7 +13,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 def test_bench_line_has_the_contract_keys():
     out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--members-per-gpu", "40000", "--steps", "3",
-                          "--warmup", "3", "--e2e-members", "8192", "--cpu-seconds", "1"],
+                          "--warmup", "3", "--e2e-members", "8192", "--cpu-seconds", "1", "--configs-scale", "0.01"],
                          capture_output=True, text=True, timeout=900)
     assert out.returncode == 0, out.stderr[-3000:]
     lines = [l for l in out.stdout.splitlines() if l.strip()]
@@ -34,3 +34,12 @@ def test_bench_line_has_the_contract_keys():
     c = d["cpu_baseline"]
     assert c["kind"] == "port" and c["cores"] >= 1 and c["value"] > 0 and "sample" in c
     assert set(d["clocks"]) >= {"sm_mhz", "sm_max_mhz", "reasons"}
+    # round 2: the link ceiling e2e is stated against, the measured peaks, the other BASELINE configurations
+    assert e["ceiling_value"] > 0 and 0 < e["frac_of_ceiling"] < 1.5 and e["pcie_ceiling_gbs"]["d2h_alone"][0] > 1
+    assert d["peaks"]["fp64_tflops"] > 20 and d["peaks"]["hbm_gbs"] > 1000
+    cfg = d["configs"]
+    for key in ("configs1_1e4_members", "configs2_1e6x4_scenario_shared_f64", "configs2_1e6x4_scenario_shared_f32",
+                "configs4_dt0.1_T_and_statistics", "configs4_dt0.1_full_output_chunk", "newton_k3"):
+        assert "error" not in cfg[key], cfg[key]
+        assert cfg[key]["kernel_ms"] > 0 and cfg[key]["value"] > 0 and cfg[key]["frac"] > 0 and "kernel_variant" in cfg[key]
+    assert c["textbook_scalar_loop"]["value"] > 0

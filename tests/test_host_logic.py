@@ -250,3 +250,21 @@ def test_vendored_reference_test_file_is_verbatim():
     ref = "/root/reference/tests/unit/test_hfcs.py"
     if os.path.exists(ref):
         assert open(ref, "rb").read() == data
+
+
+def test_shape_validation_of_scenario_inputs():
+    """e_scale must be [G][M] (a short array would be read past its end by the copy loop), and a
+    member axis that is neither M nor backed by scen_idx is an error, not a silent scenario run."""
+    from fiveeqscm_b200.concentrations import _shapes
+    G, n_t, M = 3, 10, 64
+    ok = _shapes((G, n_t, 4), (G, 17, M), (4, M), object(), None, False, (G, M))
+    assert ok[3] is True and ok[4] == 4
+    for bad in ((M,), (1, M), (G, M - 1), (G + 1, M)):
+        with pytest.raises(ValueError, match="e_scale"):
+            _shapes((G, n_t, 4), (G, 17, M), (4, M), object(), None, False, bad)
+    with pytest.raises(ValueError, match="e_scale"):
+        _shapes((G, n_t, M), (G, 17, M), (4, M), None, None, False, (G, M))      # per-member emissions: no scale
+    with pytest.raises(ValueError, match="scen_idx"):
+        _shapes((G, n_t, 5), (G, 17, M), (4, M), None, None, False)              # 5 columns, 64 members, no index
+    assert _shapes((G, n_t, 1), (G, 17, M), (4, M), None, None, False)[3] is True   # one shared column is fine
+    assert _shapes((G, n_t, M), (G, 17, M), (4, M), None, None, False)[3] is False

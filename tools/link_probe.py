@@ -27,7 +27,7 @@ def probe_all(L, local, world, dist, torch, nbytes=256 << 20, reps=8):
             if world > 1:
                 dist.barrier()
             from fiveeqscm_b200 import _abi
-            _abi.check(L.ufair_link_probe(local, nb, rows, reps, mode, g))
+            _abi.check(L.ufair_link_probe(local, nb if mode != 1 else 0, nb if mode != 0 else 0, rows, reps, g, None))
             v = torch.tensor([g[0], g[1]], dtype=torch.float64, device="cuda")
             if world > 1:
                 all_v = [torch.zeros_like(v) for _ in range(world)]
@@ -41,7 +41,7 @@ def probe_all(L, local, world, dist, torch, nbytes=256 << 20, reps=8):
                 if mode == 2 or d == key:
                     rec[d] = {"min": float(v[:, col].min()), "max": float(v[:, col].max()), "sum": float(v[:, col].sum())}
             out["%s_%s" % (name, key)] = rec
-    L.ufair_link_probe(local, 0, 0, 1, 0, g)
+    L.ufair_link_probe(local, 0, 0, 0, 1, g, None)
     return out
 
 
