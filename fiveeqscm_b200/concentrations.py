@@ -409,7 +409,7 @@ class DevicePlan:
         form is one UFAIR_FORM byte per gas, 0 everywhere = the general kernel."""
         f, g, mw, loop = C.c_uint32(), C.c_int32(), C.c_int32(), C.c_int32()
         _abi.check(self._L.ufair_kernel_variant(C.byref(self.desc), 8 if self.precision == "f64" else 4, f, g, mw, loop))
-        self.loop_variant = _abi.LOOP_NAMES[loop.value]   # "general" | "conc_driven" | "plain" | "plain_fext"
+        self.loop_variant = _abi.LOOP_NAMES[loop.value]   # one of _abi.LOOP_NAMES (UFAIR_LOOP_*)
         return tuple((f.value >> (8 * k)) & 0xff for k in range(self.n_gas)), g.value, mw.value
 
     def reset_stats(self):

@@ -43,8 +43,10 @@
 //     MW members x TT steps x NGAS gases; out-of-range rows/columns are zero-filled by the
 //     hardware, which is what makes ragged tails free), double-buffered on two mbarriers per warp.
 //     Per-member external forcing rides the same way through a 2-D map.
-//   * C / RF / T are written straight from registers with streaming (st.global.cs) stores, one
-//     aligned 256-byte run per warp and row -- nothing is re-read.
+//   * C / RF / T are written straight from registers with streaming 64-bit stores (STG.E.EF.64): with all
+//     gases of a member in one lane a warp writes one 256-byte run per row, with one gas per lane three
+//     80-byte runs; L2 merges them into full sectors (DRAM traffic 1.01x the algorithmic bytes, ncu) --
+//     nothing is re-read.
 //   * optional statistics: the per-step histogram and the moments both come from a second,
 //     HBM-speed pass over the T rows this kernel writes (stats_pass_kernel, ufair_abi.cu): block-level
 //     shared-memory histograms behind per-thread run-length merging.  Measured: the in-loop version (one
@@ -68,9 +70,11 @@
 #endif
 // FP64, default alpha mode: ensembles of at most this many members run one gas per lane (3.2x as many
 // warps: a 10^4-member ensemble fills a third of the GPU's schedulers with 32-member warps, all of them
-// with 10-member warps), larger ones all gases per lane.  Both give bit-identical results.
+// with 10-member warps), larger ones all gases per lane.  Both give bit-identical results.  Measured (ms per
+// launch, 3 gases x 736 steps; one gas per lane | all gases per lane): 10^4 members 0.38 | 0.65, 2*10^4
+// 0.64 | 0.99, 4*10^4 1.07 | 1.38, 8*10^4 2.07 | 2.22, 1.6*10^5 4.05 | 3.88, 6.4*10^5 16.2 | 14.7.
 #ifndef UFAIR_SMALL_ENSEMBLE
-#define UFAIR_SMALL_ENSEMBLE 12288
+#define UFAIR_SMALL_ENSEMBLE 100000
 #endif
 #ifndef UFAIR_GPL_ALL_F32
 #define UFAIR_GPL_ALL_F32 1
@@ -84,8 +88,8 @@
 #ifndef UFAIR_MINB_F32
 #define UFAIR_MINB_F32 (32 / UFAIR_WARPS)
 #endif
-#ifndef UFAIR_MINB_F64_GPLALL  // resident WARPS per SM, FP64 general kernel with all gases of a member in one lane
-#define UFAIR_MINB_F64_GPLALL 12
+#ifndef UFAIR_MINB_F64_GPLALL  // resident WARPS per SM, FP64 general kernel with all gases of a member in one lane:
+#define UFAIR_MINB_F64_GPLALL 8  // two per scheduler, every per-lane constant in registers (see UFAIR_REGCONST_GPLALL)
 #endif
 #ifndef UFAIR_MINB_F64_FORM  // resident WARPS per SM for the specialised (per-gas form) kernels
 #define UFAIR_MINB_F64_FORM 10
@@ -116,10 +120,13 @@
 #ifndef UFAIR_MINB_F32_GPLALL
 #define UFAIR_MINB_F32_GPLALL 12
 #endif
-// ... and for the FP64 dense kernels with all gases of a member in one lane.  Measured (ms per launch at 12
-// warps/SM): [0] 29.4, [4] 29.1, [5] 28.6 (163 registers: the alpha_val and thermal constants in registers).
+// ... and for the FP64 dense kernels with all gases of a member in one lane.  Occupancy buys nothing here --
+// 16, 14, 12, 10 and 8 resident warps per SM were all measured, and what sets the time is the length of each
+// warp's own instruction stream -- so the constants go to registers as far as the 255-register limit allows.
+// Measured (ms per launch, [REGCONST, warps/SM]): [0,16] 29.5, [0,12] 29.2, [4,12] 29.1, [5,12] 28.3, [5,10] 27.5,
+// [6,8] 28.0, [7,8] 27.0 (226 registers: alpha_val, pool and thermal constants all in registers; 21 LDS per step left).
 #ifndef UFAIR_REGCONST_GPLALL
-#define UFAIR_REGCONST_GPLALL 5
+#define UFAIR_REGCONST_GPLALL 7
 #endif
 #ifndef UFAIR_TT
 #define UFAIR_TT 8  // time steps per shared-memory tile (8 measured ~2 % faster than 4)
@@ -127,8 +134,8 @@
 #ifndef UFAIR_TT_FORM  // ... for the specialised-form kernels (32 members per warp: their tiles are 3.2x as
 #define UFAIR_TT_FORM 2  // wide, and shared memory, not registers, would otherwise cap their occupancy)
 #endif
-#ifndef UFAIR_TT_GPLALL  // ... and for the dense FP64 kernels with all gases of a member in one lane
-#define UFAIR_TT_GPLALL 1  // (measured: 1 step 29.4 ms, 2 steps 29.9, 4 steps 29.3 before the constants moved to registers)
+#ifndef UFAIR_TT_GPLALL  // ... and for the dense FP64 kernels with all gases of a member in one lane (at 8 warps per
+#define UFAIR_TT_GPLALL 8  // SM shared memory is no constraint; measured 1 step 27.1 ms, 2: 27.2, 4: 26.8, 8: 26.5)
 #endif
 
 namespace ufair {
@@ -584,24 +591,26 @@ __global__ void __launch_bounds__(kWarps * 32, min_blocks(sizeof(Real), NGAS, GP
         fx_next = __ldg(fx_scen_p + (long long)min(t + 1, n_t - 1) * a.n_scen);
       }
     }
-    Real Fg[GPL];
+    // The step runs in three passes over the gases of the lane -- alpha_val for every gas, then step_conc
+    // for every gas, then step_forc for every gas -- instead of gas by gas: the gases are independent until
+    // their forcings are added, and with the same stage of all of them next to each other in one basic
+    // block the scheduler interleaves their dependent FP64 chains (with one gas per lane the passes are
+    // the old gas-by-gas order).
+    Real Fg[GPL], e[GPL], alpha[GPL], inva[GPL], Cg[GPL];
     bool bad = false;  // some logarithm of this step has an argument outside the fast path's domain
+    // ---- inputs + alpha_val: state at t-1 -> alpha, 1/alpha
 #pragma unroll
     for (int gl = 0; gl < GPL; ++gl) {
       const int NP = form_pools(FORM, gl);
-      const unsigned TERMS = form_terms(FORM, gl);
-      Real e;
       if (EMEM) {
-        e = lds(e_addr + tt_off + (uint32_t)gl * GROW, Real());
+        e[gl] = lds(e_addr + tt_off + (uint32_t)gl * GROW, Real());
       } else {
-        e = e_next[gl] * esc[gl];
+        e[gl] = e_next[gl] * esc[gl];
         e_next[gl] = __ldg(e_scen + gl * scen_gstride + (long long)min(t + 1, n_t - 1) * a.n_scen);
       }
-      // ---- alpha_val: state at t-1 -> alpha, 1/alpha
-      Real alpha, inva;
       if (AMODE == UFAIR_ALPHA_ONE) {
-        alpha = Real(1);
-        inva = Real(1);
+        alpha[gl] = Real(1);
+        inva[gl] = Real(1);
       } else {
         const Real rho0 = HOT_SMEM ? PARG(gl, WS::G_HOT + H_RHO0) : hot[gl][H_RHO0];
         const Real rhoU = HOT_SMEM ? PARG(gl, WS::G_HOT + H_RHOU) : hot[gl][H_RHOU];
@@ -612,37 +621,42 @@ __global__ void __launch_bounds__(kWarps * 32, min_blocks(sizeof(Real), NGAS, GP
           const Real umax = HOT_SMEM ? PARG(gl, WS::G_HOT + H_UMAX) : hot[gl][H_UMAX];
           u = (u > umax) ? umax : u;
         }
-        alpha = (AMODE == UFAIR_ALPHA_SINH) ? PARG(gl, WS::G_X0) * M::sinh_pair(u, tb, nmin[gl]) : M::exp_(u, tb, nmin[gl]);
+        Real al = (AMODE == UFAIR_ALPHA_SINH) ? PARG(gl, WS::G_X0) * M::sinh_pair(u, tb, nmin[gl]) : M::exp_(u, tb, nmin[gl]);
         if (AMODE == UFAIR_ALPHA_NEWTON) {
           const Real iirf = (u - PARG(gl, WS::G_X0 + 1)) * PARG(gl, WS::G_X0);
           const Real invc = PARG(gl, WS::G_X0 + 2);
-#ifdef UFAIR_EXP_NEWTON_K  // experiment: what a compile-time (unrolled) iteration count is worth over the run-time loop
-#pragma unroll
+#ifdef UFAIR_EXP_NEWTON_K  // experiment: what a compile-time (unrolled) iteration count is worth over the run-time
+#pragma unroll             // loop (measured, K = 3, configs[3] shard: 90.1 -> 87.6 ms)
           for (int it = 0; it < UFAIR_EXP_NEWTON_K; ++it) {
 #else
           for (int it = 0; it < a.newton_iters; ++it) {
 #endif
-            const Real ia = M::rcp(alpha);
+            const Real ia = M::rcp(al);
             Real f = -iirf, fp = 0;
 #pragma unroll
             for (int q = 0; q < NP; ++q) {
               const Real z = PK0(gl, q) * hdt * ia;
               const Real mz = M::decay(z, tb);
               const Real at = PKA(gl, q) * invc;  // a_i tau_i
-              f = fma(at * alpha, mz, f);
+              f = fma(at * al, mz, f);
               fp = fma(at, mz - z * (Real(1) - mz), fp);
             }
-            const Real an = alpha - f * M::rcp(fp);
-            alpha = M::fmax_(an, Real(0.5) * alpha);
+            const Real an = al - f * M::rcp(fp);
+            al = M::fmax_(an, Real(0.5) * al);
           }
         }
-        inva = M::rcp(alpha);
+        alpha[gl] = al;
+        inva[gl] = M::rcp(al);
       }
-      // ---- step_conc: relax each pool toward its equilibrium  E alpha c a_i tau_i
+    }
+    // ---- step_conc: relax each pool toward its equilibrium  E alpha c a_i tau_i
+#pragma unroll
+    for (int gl = 0; gl < GPL; ++gl) {
+      const int NP = form_pools(FORM, gl);
       Real mq[4];
 #pragma unroll
       for (int q = 0; q < 4; ++q)
-        if (q < NP) mq[q] = (AMODE == UFAIR_ALPHA_ONE) ? PK0(gl, q) : M::decay(PK0(gl, q) * inva, tb);
+        if (q < NP) mq[q] = (AMODE == UFAIR_ALPHA_ONE) ? PK0(gl, q) : M::decay(PK0(gl, q) * inva[gl], tb);
       if (INV) {
         // concentration-driven gas: `e` is the target C; step_conc is linear in E, so
         //   E = (C_target - C0 - sum R_i (1 - m_i)) / (alpha sum m_i c a_i tau_i)
@@ -653,33 +667,37 @@ __global__ void __launch_bounds__(kWarps * 32, min_blocks(sizeof(Real), NGAS, GP
             keep += fma(-mq[q], R[gl][q], R[gl][q]);
             gain = fma(mq[q], PKA(gl, q), gain);
           }
-        const Real e_inv = ((e - PARG(gl, G_C0)) - keep) * M::rcp(gain * alpha);
-        if ((a.conc_driven >> (g0 + gl)) & 1) e = e_inv;
-        if (wm & UFAIR_OUT_E) st_stream(pC + dE + gl * gstride, e);
+        const Real e_inv = ((e[gl] - PARG(gl, G_C0)) - keep) * M::rcp(gain * alpha[gl]);
+        if ((a.conc_driven >> (g0 + gl)) & 1) e[gl] = e_inv;
+        if (wm & UFAIR_OUT_E) st_stream(pC + dE + gl * gstride, e[gl]);
       }
-      const Real ea = e * alpha;
+      const Real ea = e[gl] * alpha[gl];
 #pragma unroll
       for (int q = 0; q < 4; ++q)
         if (q < NP) R[gl][q] = fma(mq[q], fma(ea, PKA(gl, q), -R[gl][q]), R[gl][q]);
-      Gcum[gl] = fma(e, dt, Gcum[gl]);
+      Gcum[gl] = fma(e[gl], dt, Gcum[gl]);
       sumR[gl] = sum_pools(R[gl], NP);
-      const Real C = PARG(gl, G_C0) + sumR[gl];
-      // ---- step_forc: F = f2 (C - C0) + f1 ln(C / C0) + f3 (sqrt C - sqrt C0), with C - C0 = sumR and
-      // C / C0 = 1 + sumR / C0.  The logarithm runs its branch-free fast path for every gas of the lane
-      // first (one basic block: the gases interleave); arguments outside its domain are patched after
-      // the gas loop.  The sqrt VALUE is masked, not the product, so that a zero coefficient with a NaN
-      // function value still contributes exactly zero.
+      Cg[gl] = PARG(gl, G_C0) + sumR[gl];
+      // (PLAIN: the lane predicates themselves, not bits re-tested every step)
+      if (ALLOUT ? active : PLAIN ? st_c : (wm & UFAIR_OUT_C) != 0) st_stream(pC + gl * gstride, Cg[gl]);
+      if (!PLAIN && (wm & UFAIR_OUT_ALPHA)) st_stream(pC + dA + gl * gstride, alpha[gl]);
+    }
+    // ---- step_forc: F = f2 (C - C0) + f1 ln(C / C0) + f3 (sqrt C - sqrt C0), with C - C0 = sumR and
+    // C / C0 = 1 + sumR / C0.  The logarithm runs its branch-free fast path for every gas (a special-case
+    // branch per logarithm would split the gases into separate basic blocks); arguments outside its domain
+    // are patched after the loop.  The sqrt VALUE is masked, not the product, so that a zero coefficient
+    // with a NaN function value still contributes exactly zero.
+#pragma unroll
+    for (int gl = 0; gl < GPL; ++gl) {
+      const unsigned TERMS = form_terms(FORM, gl);
       Real F = (TERMS & UFAIR_TERM_LIN) ? PARG(gl, G_F2) * sumR[gl] : Real(0);
       if (need_log[gl]) {
         const Real y = fma(sumR[gl], PARG(gl, G_INVC0), Real(1));
         F = fma(PARG(gl, G_F1), M::log_fast(y), F);
         bad = bad || M::not_normal(y);
       }
-      if (need_sqrt[gl]) F = fma(PARG(gl, G_F3), M::mask(M::sqrt_(C) - PARG(gl, G_SQRTC0), mk3[gl]), F);
+      if (need_sqrt[gl]) F = fma(PARG(gl, G_F3), M::mask(M::sqrt_(Cg[gl]) - PARG(gl, G_SQRTC0), mk3[gl]), F);
       Fg[gl] = F;
-      // (PLAIN: the lane predicates themselves, not bits re-tested every step)
-      if (ALLOUT ? active : PLAIN ? st_c : (wm & UFAIR_OUT_C) != 0) st_stream(pC + gl * gstride, C);
-      if (!PLAIN && (wm & UFAIR_OUT_ALPHA)) st_stream(pC + dA + gl * gstride, alpha);
     }
     if (__builtin_expect(bad, 0)) {  // never on a physical trajectory: redo those gases' forcing with the special values
 #pragma unroll

@@ -58,8 +58,14 @@ template <> struct Math<double> {
   // holds the FP64 pipe ~3.7 cycles, with one ~2.3, with three vector registers ~2.5.
   static constexpr double kMagic = 6755399441055744.0;
 
-  // expm1(r) for |r| <= ln2/2:  r + r^2 Q(r)
-  static __device__ __forceinline__ double expm1_reduced(double r) {
+  // Operand kinds matter on the FP64 pipe (measured on B200, tools/micro/dfma_forms.cu): a DFMA whose three
+  // sources are three DIFFERENT vector registers holds the pipe for 3 cycles, every other FP64 instruction
+  // (a constant-bank / uniform-register / immediate operand, or a register used twice; DADD; DMUL) for 2.
+  // The Horner steps below are (register, register, constant); the closing steps are arranged so that they
+  // use a register twice or an immediate instead of three registers.
+
+  // Q(r) of expm1(r) = r + r^2 Q(r), |r| <= ln2/2
+  static __device__ __forceinline__ double expm1_q(double r) {
     double q = cExpQ[9];
     q = fma(q, r, cExpQ[8]);
     q = fma(q, r, cExpQ[7]);
@@ -69,8 +75,12 @@ template <> struct Math<double> {
     q = fma(q, r, cExpQ[3]);
     q = fma(q, r, cExpQ[2]);
     q = fma(q, r, cExpQ[1]);
-    q = fma(q, r, cExpQ[0]);
-    return fma(r * r, q, r);
+    return fma(q, r, cExpQ[0]);
+  }
+  // expm1(r) = r + r (r Q): the closing DFMA reads r twice (2 pipe cycles; r^2 Q + r would read three registers)
+  static __device__ __forceinline__ double expm1_reduced(double r) {
+    const double q = expm1_q(r);
+    return fma(r, r * q, r);
   }
 
   // y = n ln2 + r with n = rint(y log2 e); returns r, n through `n`
@@ -106,7 +116,7 @@ template <> struct Math<double> {
   static __device__ __forceinline__ double exp_(double u, uint32_t, int nmin = -40) {
     int n;
     double r = reduce(u, n);
-    double v = 1.0 + expm1_reduced(r);
+    double v = fma(r, fma(r, expm1_q(r), 1.0), 1.0);  // 1 + r (1 + r Q): two immediate-operand DFMAs
     n = max(min(n, 40), nmin);
     return __hiloint2double(__double2hiint(v) + (n << 20), __double2loint(v));
   }
@@ -175,6 +185,7 @@ template <> struct Math<double> {
     L = fma(L, w, cLogL[1]);
     L = fma(L, w, cLogL[0]);
     double ed = __hiloint2double(0x43300000, e ^ 0x80000000) - cK[6];  // (double)e
+    // (s (2 + w L) would save a DMUL and a DFMA, but rounding 2 + w L costs the logarithm about one more ulp: it failed the 2.5-ulp test)
     double t = fma(s * w, L, ed * cK[5]);
     t = fma(2.0, s, t);
     return fma(ed, cK[4], t);

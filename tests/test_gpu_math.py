@@ -42,6 +42,10 @@ def test_decay_f64(rng):
     ref = -np.expm1(-_ld(x))
     assert _ulps(got, ref) <= 2.0
     assert got[-5] == 0.0 and got[-1] == 1.0
+    # saturation: exactly 1 all the way to the top of the routine's domain (x < 1.4e9; the integrator keeps
+    # x = (dt / tau) / alpha below 7.6e8 by raising alpha's lower saturation per lane -- ADVICE r1)
+    big = _probe("decay", np.array([1e3, 1e6, 1e8, 7.6e8, 1.3e9]))
+    assert np.all(big == 1.0)
 
 
 def test_exp_f64(rng):

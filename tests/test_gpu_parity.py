@@ -580,3 +580,26 @@ def test_loop_variant_selection(api):
     assert loop(outputs=("T",)) == "plain_subset" and loop(outputs=(), stats=api.HistSpec(), f_ext=fx) == "plain_subset"
     assert loop(outputs=("T",), alpha_mode="sinh") == "general"
     assert loop(conc_driven=True) == "conc_driven" and loop(outputs=("C", "RF", "T", "E")) == "conc_driven"
+
+
+def test_alpha_saturation_keeps_the_decay_argument_in_its_domain(api):
+    """with alpha driven to its lower saturation (iIRF hugely negative) and a fast pool,
+    x = (dt / tau) / alpha used to run past the range-reduction's 32-bit integer and the pools blew up
+    silently.  alpha's floor is now raised per lane so that x stays below 7.6e8: the run stays finite, the
+    fast pools simply equilibrate (m = 1), and the concentrations stay pinned near C0."""
+    import torch
+    ens = ensemble(64, n_t=30, dense=True)
+    gp = ens["gas_params"].copy()
+    gp[:, _abi.GP_R0] = -5000.0                      # alpha -> exp(-hundreds): saturates
+    gp[0, _abi.GP_TAU0 + 3] = 0.002                  # dt / tau = 500
+    for mode in ("exp", "newton"):
+        res = api.run_ensemble(to_dev(ens["E"]), to_dev(gp), to_dev(ens["thermal_params"]), alpha_mode=mode, newton_iters=3,
+                               outputs=("C", "RF", "T", "alpha"))
+        torch.cuda.synchronize()
+        for k in ("C", "RF", "T", "alpha", "state"):
+            assert bool(torch.isfinite(getattr(res, k)).all()), (mode, k)
+        if mode == "exp":   # (Newton's safeguarded steps walk alpha back up from the saturated seed)
+            al = to_np(res.alpha)
+            assert al.max() < 1e-6 and al.min() > 0.0
+            C0 = gp[:, _abi.GP_C0][:, None, :]
+            assert np.all(np.abs(to_np(res.C) - C0) < 1e-2 * C0)

@@ -110,3 +110,42 @@ def test_sharded_ensemble_statistics_equal_the_single_gpu_run(api):
     pw = stats.percentiles_device(whole.hist, spec.lo, spec.hi, (5, 50, 95))
     ps = stats.percentiles_device(a.hist + b.hist, spec.lo, spec.hi, (5, 50, 95))
     assert torch.equal(pw, ps)
+
+
+def test_packed_statistics_layout_round_trips_and_reduces_like_the_plain_one(api):
+    """The cross-GPU reduce works on two packed buffers (ufair_stats_finalize_packed: counts as doubles + moment
+    sums -> SUM; max and -min -> MAX).  On one GPU: packed -> unpack equals the plain finalize bit for bit, and
+    'reducing' two shards' packed buffers the way the collectives would (elementwise sum / max) and unpacking
+    gives the single run's histogram and extrema bit for bit -- the arithmetic of dist.StatsReducer without NCCL."""
+    import ctypes as C
+
+    import torch
+    L = _abi.lib()
+    M, n_t, seed = 5000, 60, 3
+    scen_E = to_dev(P.scenario_emissions(n_t))
+    spec = api.HistSpec(lo=-1.0, hi=6.0, bins=256)
+
+    def packed(first, n):
+        gp, tp, esc, scen = P.sample_on_device(n, seed, first_member=first)
+        plan = api.DevicePlan(scen_E, gp, tp, scen_idx=scen, e_scale=esc, stats=spec, outputs=("T",), return_state=False)
+        plan.reset_stats(); plan.launch(); plan.stats_pass(); plan.finalize_stats()
+        sums = torch.empty(n_t, spec.bins + 2, dtype=torch.float64, device="cuda")
+        ext = torch.empty(n_t, 2, dtype=torch.float64, device="cuda")
+        _abi.check(L.ufair_stats_finalize_packed(C.byref(plan.desc), sums.data_ptr(), ext.data_ptr(), None))
+        torch.cuda.synchronize()
+        return plan.result, sums, ext
+
+    def unpack(sums, ext):
+        hist = torch.empty(n_t, spec.bins, dtype=torch.int64, device="cuda")
+        mom = torch.empty(n_t, 4, dtype=torch.float64, device="cuda")
+        _abi.check(L.ufair_stats_unpack(sums.data_ptr(), ext.data_ptr(), n_t, spec.bins, hist.data_ptr(), mom.data_ptr(), None))
+        torch.cuda.synchronize()
+        return hist, mom
+
+    whole, s_w, e_w = packed(0, M)
+    h, m = unpack(s_w, e_w)
+    assert torch.equal(h, whole.hist) and torch.equal(m, whole.moments)
+    (ra, s_a, e_a), (rb, s_b, e_b) = packed(0, 2048), packed(2048, M - 2048)
+    h2, m2 = unpack(s_a + s_b, torch.maximum(e_a, e_b))
+    assert torch.equal(h2, whole.hist) and torch.equal(m2[:, 2:], whole.moments[:, 2:])
+    assert torch.allclose(m2[:, :2], whole.moments[:, :2], rtol=1e-12, atol=1e-12)
