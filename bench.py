@@ -65,9 +65,10 @@ def parse():
     ap.add_argument("--members-per-gpu", type=int, default=1_250_000)
     ap.add_argument("--n-t", type=int, default=736)
     ap.add_argument("--precision", default="f64", choices=["f64", "f32"])
-    ap.add_argument("--e2e-members", type=int, default=786432, help="members per GPU of the e2e leg (0: the whole shard; "
-                    "the default is 63 %% of it because page-locking the shard's 74 GB of host buffers takes ~35 s per rank, "
-                    "which would be most of the run; always cut down to a third of the host's free memory)")
+    ap.add_argument("--e2e-members", type=int, default=-1, help="members per GPU of the e2e leg (0: the whole shard; default: "
+                    "786432 at N <= 2, 393216 at N = 4, 262144 at N = 8 -- page-locking the shard's 74 GB of host buffers takes "
+                    "~35 s per rank alone and more with 8 ranks at once, which would be most of the run, and at N >= 4 this "
+                    "platform's shared host link makes the same bytes take 3-5x as long; always within a third of free host memory)")
     ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--e2e-chunk", type=int, default=16384, help="members per chunk of the host pipeline")
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="target CPU work for the cpu_baseline sample")
@@ -659,7 +660,8 @@ def main():
     # ---- e2e: the public host-buffer API, pinned host inputs, H2D + kernel + D2H of every output
     if not args.no_e2e:
         row_bytes = (N_GAS * n_t + N_GAS * 17 + 4) * es + ((2 * N_GAS + 1) * n_t + 18) * es   # host bytes per member
-        Me = min(args.e2e_members, M) if args.e2e_members > 0 else M
+        auto = {1: 786432, 2: 786432, 4: 393216}.get(world, 262144)
+        Me = M if args.e2e_members == 0 else min(args.e2e_members if args.e2e_members > 0 else auto, M)
         try:
             avail = [int(ln.split()[1]) * 1024 for ln in open("/proc/meminfo") if ln.startswith("MemAvailable")][0]
             fit = int(avail / 3 / world / row_bytes) // 1024 * 1024
@@ -770,6 +772,39 @@ def main():
                     "what": "same host inputs, outputs=(): only the per-step T histogram and moments return to the host"}
             except Exception as exc:
                 line["e2e_statistics_only"] = {"error": repr(exc)}
+        # secondary: the same ensemble the way configs[3] would be fed in production -- the emissions ARE scenario rows
+        # times a per-member scale, so the host holds the 4-scenario table, an index and a scale per member and the
+        # parameters; nothing else crosses the link, only the statistics come back
+        if spec is not None and not args.sparse:
+            try:
+                ws.close()
+                ws = conc.Workspace(local, 262144)
+                from fiveeqscm_b200 import params as P
+                gp3, tp3, esc3, idx3 = P.sample_on_device(Me, 20261018, first_member=rank * M, n_scen=4, dense_pools=True,
+                                                          precision=args.precision)
+                scen_h = torch.from_numpy(P.scenario_emissions(n_t)).to(hdt).pin_memory()
+                gp3h, tp3h, esc3h = pin(gp3), pin(tp3), pin(esc3)
+                idx3h = torch.empty(idx3.shape, dtype=torch.int32, pin_memory=True); idx3h.copy_(idx3)
+                out3 = conc.pinned_result(N_GAS, n_t, Me, outputs=(), stats=spec, precision=args.precision, return_state=False)
+                call3 = lambda: conc.run_ensemble(scen_h, gp3h, tp3h, scen_idx=idx3h.numpy(), e_scale=esc3h, stats=spec, outputs=(),
+                                                  precision=args.precision, workspace=ws, out=out3, return_state=False)
+                call3()
+                barrier()
+                t0 = time.perf_counter()
+                for _ in range(args.e2e_steps):
+                    call3()
+                el3 = torch.tensor([time.perf_counter() - t0], device="cuda", dtype=torch.float64)
+                if world > 1:
+                    dist.all_reduce(el3, op=dist.ReduceOp.MAX)
+                up3 = (N_GAS * 17 + 4 + N_GAS) * Me * es + Me * 4 + N_GAS * n_t * 4 * es
+                line["e2e_scenario_inputs"] = {
+                    "value": float(Me) * n_t * n_gpus * args.e2e_steps / float(el3.item()), "unit": "member-timesteps/s",
+                    "h2d_bytes_per_step": up3, "d2h_bytes_per_step": n_t * spec.bins * 8 + n_t * 32,
+                    "what": "host inputs = scenario table [3][n_t][4] + per-member scenario index, emission scale and parameters "
+                            "(%.2f B per member-step), outputs = per-step histogram and moments; chunks of 262144 members" % (up3 / (float(Me) * n_t))}
+                del gp3, tp3, esc3, idx3
+            except Exception as exc:
+                line["e2e_scenario_inputs"] = {"error": repr(exc)}
         ws.close()
         del Eh, gph, tph, out
     else:
