@@ -1,6 +1,7 @@
 // ufair_abi.cu -- extern "C" entry points of libufair.so (include/ufair.h): argument checking,
 // dispatch to the fused integrator instantiations, and the small kernels either side of it
 // (statistics reset/finalise, g_1/g_0, k_q, the reference's one-box pulse, peak microbenchmarks).
+#include <stdlib.h>
 #include <cuda.h>
 #include <cuda_runtime.h>
 #include <math.h>
@@ -94,6 +95,14 @@ template <typename Real> static KArgs<Real> make_args(const ufair_desc* d) {
   a.out_mask = d->out_mask;
   a.stats = d->stats;
   a.newton_iters = d->newton_iters;
+#ifdef UFAIR_DEBUG_BOUNDS
+  {  // negative control of the in-kernel bounds checks: UFAIR_DEBUG_TRIP=1 must make a full-length run trap
+    const char* trip = getenv("UFAIR_DEBUG_TRIP");
+    a.dbg_cut = (trip && trip[0] == '1') ? 1 : 0;
+  }
+#else
+  a.dbg_cut = 0;
+#endif
   a.clamp = (d->iirf_max > 0.0 && isfinite(d->iirf_max)) ? 1 : 0;
   a.dt = d->dt;
   a.h = d->iirf_h;

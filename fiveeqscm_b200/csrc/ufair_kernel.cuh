@@ -214,6 +214,7 @@ template <typename Real> struct KArgs {
   Real* oA;
   Real* oE;
   int conc_driven;  // bit g: gas g's input rows are target concentrations (INV kernels only)
+  int dbg_cut;      // UFAIR_DEBUG_BOUNDS builds only: rows the store check pretends are missing (its negative control)
   Real* state_out;
 };
 
@@ -271,6 +272,26 @@ __device__ __forceinline__ void sts(uint32_t a, float v) { asm volatile("st.shar
 __device__ __forceinline__ void pin(uint32_t& x) { asm volatile("" : "+r"(x)); }
 
 template <typename Real> __device__ __forceinline__ void st_stream(Real* p, Real v) { __stcs(p, v); }
+
+// -DUFAIR_DEBUG_BOUNDS (libufair_dbg.so, `make debug`; tests/test_gpu_guard.py runs the ragged cases on it):
+// every output store must land inside its array, in a column below n_member, and every read of the
+// shared-memory rings inside the box the TMA delivered for the current stage -- otherwise the kernel traps.
+// compute-sanitizer is closed on the GPU pool this was developed on; this is the in-kernel stand-in.
+#ifdef UFAIR_DEBUG_BOUNDS
+#define UFAIR_CHECK_ST(base, nrows, p)                                                                    \
+  do {                                                                                                    \
+    const long long off_ = (long long)((p) - (base));                                                     \
+    if ((base) == nullptr || off_ < 0 || off_ >= ((long long)(nrows) - a.dbg_cut) * ld || off_ % ld >= a.n_member) __trap(); \
+  } while (0)
+#define UFAIR_CHECK_RING(addr, ring0, stage_bytes, box_bytes)                                             \
+  do {                                                                                                    \
+    const uint32_t off_ = (addr) - (ring0);                                                               \
+    if ((addr) < (ring0) || off_ >= (uint32_t)kStages * (stage_bytes) || off_ % (stage_bytes) + ES > (box_bytes)) __trap(); \
+  } while (0)
+#else
+#define UFAIR_CHECK_ST(base, nrows, p) ((void)0)
+#define UFAIR_CHECK_RING(addr, ring0, stage_bytes, box_bytes) ((void)0)
+#endif
 
 // per-lane derived constants.  Rows G_* exist once per gas the lane integrates; the five `hot` ones
 // (needed first in a step, on the critical path into alpha) live in registers when a lane carries
@@ -585,7 +606,10 @@ __global__ void __launch_bounds__(kWarps * 32, min_blocks(sizeof(Real), NGAS, GP
   auto step = [&](const int t, const uint32_t tt_off) {
     Real fx = 0;
     if (fx_any) {  // one uniform branch when there is no external forcing at all
-      if (fx_member) fx = lds(f_addr + tt_off, Real());
+      if (fx_member) {
+        UFAIR_CHECK_RING(f_addr + tt_off, wbase + WS::off_f, WS::f_stage, WS::f_box);
+        fx = lds(f_addr + tt_off, Real());
+      }
       if (fx_scen) {
         fx = fx_next;
         fx_next = __ldg(fx_scen_p + (long long)min(t + 1, n_t - 1) * a.n_scen);
@@ -603,6 +627,7 @@ __global__ void __launch_bounds__(kWarps * 32, min_blocks(sizeof(Real), NGAS, GP
     for (int gl = 0; gl < GPL; ++gl) {
       const int NP = form_pools(FORM, gl);
       if (EMEM) {
+        UFAIR_CHECK_RING(e_addr + tt_off + (uint32_t)gl * GROW, wbase + WS::off_e, WS::e_stage, WS::e_box);
         e[gl] = lds(e_addr + tt_off + (uint32_t)gl * GROW, Real());
       } else {
         e[gl] = e_next[gl] * esc[gl];
@@ -669,7 +694,10 @@ __global__ void __launch_bounds__(kWarps * 32, min_blocks(sizeof(Real), NGAS, GP
           }
         const Real e_inv = ((e[gl] - PARG(gl, G_C0)) - keep) * M::rcp(gain * alpha[gl]);
         if ((a.conc_driven >> (g0 + gl)) & 1) e[gl] = e_inv;
-        if (wm & UFAIR_OUT_E) st_stream(pC + dE + gl * gstride, e[gl]);
+        if (wm & UFAIR_OUT_E) {
+          UFAIR_CHECK_ST(a.oE, (long long)NGAS * n_t, pC + dE + gl * gstride);
+          st_stream(pC + dE + gl * gstride, e[gl]);
+        }
       }
       const Real ea = e[gl] * alpha[gl];
 #pragma unroll
@@ -679,8 +707,14 @@ __global__ void __launch_bounds__(kWarps * 32, min_blocks(sizeof(Real), NGAS, GP
       sumR[gl] = sum_pools(R[gl], NP);
       Cg[gl] = PARG(gl, G_C0) + sumR[gl];
       // (PLAIN: the lane predicates themselves, not bits re-tested every step)
-      if (ALLOUT ? active : PLAIN ? st_c : (wm & UFAIR_OUT_C) != 0) st_stream(pC + gl * gstride, Cg[gl]);
-      if (!PLAIN && (wm & UFAIR_OUT_ALPHA)) st_stream(pC + dA + gl * gstride, alpha[gl]);
+      if (ALLOUT ? active : PLAIN ? st_c : (wm & UFAIR_OUT_C) != 0) {
+        UFAIR_CHECK_ST(a.oC, (long long)NGAS * n_t, pC + gl * gstride);
+        st_stream(pC + gl * gstride, Cg[gl]);
+      }
+      if (!PLAIN && (wm & UFAIR_OUT_ALPHA)) {
+        UFAIR_CHECK_ST(a.oA, (long long)NGAS * n_t, pC + dA + gl * gstride);
+        st_stream(pC + dA + gl * gstride, alpha[gl]);
+      }
     }
     // ---- step_forc: F = f2 (C - C0) + f1 ln(C / C0) + f3 (sqrt C - sqrt C0), with C - C0 = sumR and
     // C / C0 = 1 + sumR / C0.  The logarithm runs its branch-free fast path for every gas (a special-case
@@ -718,7 +752,10 @@ __global__ void __launch_bounds__(kWarps * 32, min_blocks(sizeof(Real), NGAS, GP
     Real Fsum = 0;
 #pragma unroll
     for (int gl = 0; gl < GPL; ++gl) {
-      if (ALLOUT ? active : PLAIN ? st_rf : (wm & UFAIR_OUT_RF) != 0) st_stream(pRF + gl * gstride, Fg[gl]);
+      if (ALLOUT ? active : PLAIN ? st_rf : (wm & UFAIR_OUT_RF) != 0) {
+        UFAIR_CHECK_ST(a.oRF, (long long)NGAS * n_t, pRF + gl * gstride);
+        st_stream(pRF + gl * gstride, Fg[gl]);
+      }
       Fsum = (gl == 0) ? Fg[gl] : Fsum + Fg[gl];
     }
     pC += ld;
@@ -742,7 +779,10 @@ __global__ void __launch_bounds__(kWarps * 32, min_blocks(sizeof(Real), NGAS, GP
     S1 = s1;
     Ssum = Snew;
     Tprev = T;
-    if (ALLOUT ? owner : PLAIN ? st_t : (wm & UFAIR_OUT_T) != 0) st_stream(pT, T);
+    if (ALLOUT ? owner : PLAIN ? st_t : (wm & UFAIR_OUT_T) != 0) {
+      UFAIR_CHECK_ST(a.oT, (long long)n_t, pT);
+      st_stream(pT, T);
+    }
     pT += ld;
   };
 

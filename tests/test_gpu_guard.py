@@ -206,3 +206,44 @@ def test_host_pipeline_with_a_chunk_that_does_not_divide_M(prec):
     ref = co.oxfair(ens["E"], ens["gas_params"], ens["thermal_params"])
     T = b["oT"].data().astype(np.float64)
     assert (field_relerr(T, ref["T"], floor=0.01) < 1e-10) if prec == "f64" else (np.max(np.abs(T - ref["T"])) < 1e-4)
+
+
+# ------------------------------------------------------------------ the checked build (libufair_dbg.so)
+_DBG = __import__("os").path.join(__import__("os").path.dirname(_abi.lib_path()), "libufair_dbg.so")
+_TRIP = """
+import numpy as np, torch
+from fiveeqscm_b200 import concentrations as api
+from tests.util import ensemble, to_dev
+ens = ensemble(70, n_t=9)
+res = api.run_ensemble(to_dev(ens["E"]), to_dev(ens["gas_params"]), to_dev(ens["thermal_params"]))
+torch.cuda.synchronize()
+print("completed")
+"""
+
+
+@pytest.mark.skipif(not __import__("os").path.exists(_DBG), reason="libufair_dbg.so not built (make -C fiveeqscm_b200/csrc debug)")
+def test_debug_bounds_build_never_traps_and_its_checks_are_live():
+    """The same library compiled with -DUFAIR_DEBUG_BOUNDS traps on any output store outside its array
+    (or in a column >= n_member) and on any read of the shared-memory emission / forcing rings outside
+    the box the TMA delivered.  The ragged cases of this file and of the parity suite run on it in a
+    subprocess (a trap poisons the CUDA context) and must pass; then the negative control: with
+    UFAIR_DEBUG_TRIP=1 the store check pretends the last row of every array is missing, and the very
+    same run must die with a launch failure -- so the checks are really compiled in and reached."""
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, UFAIR_LIB=_DBG, PYTHONPATH=root)
+    env.pop("UFAIR_DEBUG_TRIP", None)
+    sel = ["tests/test_gpu_guard.py", "tests/test_gpu_parity.py::test_ragged_member_counts",
+           "tests/test_gpu_parity.py::test_modes_and_gas_counts", "tests/test_gpu_parity.py::test_scenario_shared_emissions_and_forcing",
+           "tests/test_gpu_parity.py::test_subannual_timestep", "tests/test_gpu_inverse.py", "tests/test_gpu_forms.py"]
+    r = subprocess.run([sys.executable, "-m", "pytest", "-q", "-x", "-m", "gpu", "-k", "not debug_bounds", "-p", "no:cacheprovider"] + sel,
+                       cwd=root, env=env, capture_output=True, text=True, timeout=1500)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]
+    ok = subprocess.run([sys.executable, "-c", _TRIP], cwd=root, env=env, capture_output=True, text=True, timeout=600)
+    assert ok.returncode == 0 and "completed" in ok.stdout, ok.stderr[-2000:]
+    trip = subprocess.run([sys.executable, "-c", _TRIP], cwd=root, env=dict(env, UFAIR_DEBUG_TRIP="1"), capture_output=True,
+                          text=True, timeout=600)
+    assert trip.returncode != 0 and "completed" not in trip.stdout
+    assert "trap" in trip.stderr.lower() or "launch fail" in trip.stderr.lower() or "cuda" in trip.stderr.lower(), trip.stderr[-2000:]
