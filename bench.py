@@ -778,7 +778,9 @@ def main():
         if spec is not None and not args.sparse:
             try:
                 ws.close()
-                ws = conc.Workspace(local, 262144)
+                chunk3 = conc.auto_chunk_members(N_GAS, n_t, e_member=False, fext_member=False, outputs=(), return_state=False,
+                                                 e_scale=True, precision=args.precision)   # what run_ensemble picks by itself
+                ws = conc.Workspace(local, chunk3)
                 from fiveeqscm_b200 import params as P
                 gp3, tp3, esc3, idx3 = P.sample_on_device(Me, 20261018, first_member=rank * M, n_scen=4, dense_pools=True,
                                                           precision=args.precision)
@@ -801,7 +803,8 @@ def main():
                     "value": float(Me) * n_t * n_gpus * args.e2e_steps / float(el3.item()), "unit": "member-timesteps/s",
                     "h2d_bytes_per_step": up3, "d2h_bytes_per_step": n_t * spec.bins * 8 + n_t * 32,
                     "what": "host inputs = scenario table [3][n_t][4] + per-member scenario index, emission scale and parameters "
-                            "(%.2f B per member-step), outputs = per-step histogram and moments; chunks of 262144 members" % (up3 / (float(Me) * n_t))}
+                            "(%.2f B per member-step), outputs = per-step histogram and moments; chunks of %d members (the library's own choice for a "
+                            "kernel-bound call), the first ones shorter" % (up3 / (float(Me) * n_t), chunk3)}
                 del gp3, tp3, esc3, idx3
             except Exception as exc:
                 line["e2e_scenario_inputs"] = {"error": repr(exc)}

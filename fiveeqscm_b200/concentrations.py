@@ -175,17 +175,44 @@ def _with_E(outputs, conc_driven):
     return outputs + ("E",) if driven and "E" not in outputs else outputs
 
 
+def _any_nonzero(row) -> bool:
+    """Is any element of a 1-D array non-zero?  Dense parameter sets answer from the first element; an all-zero
+    row costs one pass without a temporary (the comparison ``row != 0`` allocated one per row: 8 ms per call on a
+    786 432-member ensemble, on the critical path of every host-pipeline call)."""
+    return bool(row.size) and (bool(row[0] != 0) or bool(np.count_nonzero(row)))
+
+
 def _detect_form_host(gp, state_in):
     """gas_form from HOST parameter arrays: the numpy twin of ufair_detect_form_* (same rule)."""
     out = []
     for g in range(gp.shape[0]):
-        used = [bool(np.any(gp[g, _abi.GP_A0 + q] != 0) or (state_in is not None and np.any(state_in[5 * g + q] != 0)))
+        used = [_any_nonzero(gp[g, _abi.GP_A0 + q]) or (state_in is not None and _any_nonzero(state_in[5 * g + q]))
                 for q in range(1, 4)]
         n_pool = 4 if used[2] else 3 if used[1] else 2 if used[0] else 1
         terms = sum(bit for bit, row in ((_abi.TERM_LOG, _abi.GP_F1), (_abi.TERM_LIN, _abi.GP_F2),
-                                         (_abi.TERM_SQRT, _abi.GP_F3)) if np.any(gp[g, row] != 0))
+                                         (_abi.TERM_SQRT, _abi.GP_F3)) if _any_nonzero(gp[g, row]))
         out.append(_abi.form(n_pool, terms or _abi.TERM_LIN))
     return out
+
+
+def auto_chunk_members(n_gas, n_t, *, e_member, fext_member, outputs, return_state=True, state_in=False, e_scale=False,
+                       precision="f64") -> int:
+    """Members per chunk of the host pipeline when the caller does not say.  What matters is which side of the
+    pipeline a member keeps busy longer: the host link (bytes per member up or down at ~50 GB/s) or the integrator
+    (~10 ns per member and 1000 gas-steps in FP64, a third of that in FP32).  Link-bound calls -- per-member emissions
+    in, trajectories out -- want SMALL chunks (16 384: the fill and drain of the pipeline are one chunk each, and the
+    link is busy whatever the kernel's efficiency); kernel-bound calls -- scenario-table inputs, statistics or T
+    only out -- want chunks that fill the GPU for several waves (131 072; measured 1.8 / 2.2 / 2.2 / 1.9e10
+    member-steps/s at 32 768 / 131 072 / 262 144 / 786 432 on a 786 432-member call)."""
+    es = 8 if precision == "f64" else 4
+    gt = n_gas * n_t
+    up = (gt if e_member else 0) + (n_t if fext_member else 0) + n_gas * _abi.GP_COUNT + _abi.TP_COUNT + \
+        (n_gas if e_scale else 0) + (_abi.state_rows(n_gas) if state_in else 0)
+    down = sum(gt for o in ("C", "RF", "alpha", "E") if o in outputs) + (n_t if "T" in outputs else 0) + \
+        (_abi.state_rows(n_gas) if return_state else 0)
+    link_ns = max(up, down) * es / 50.0                       # ns per member at 50 GB/s, the busier direction
+    kernel_ns = gt * (0.010 if precision == "f64" else 0.0035)   # ns per member: 27 ms / 9 ms per 1.25e6 x 736 x 3 on B200
+    return 16384 if link_ns >= kernel_ns else 131072
 
 
 def _form_byte(f) -> int:
@@ -211,7 +238,7 @@ def _form_byte(f) -> int:
 def run_ensemble(emissions, gas_params, thermal_params, *, dt=1.0, scen_idx=None, e_scale=None, f_ext=None,
                  fext_per_member=False, state_in=None, alpha_mode="exp", newton_iters=0, iirf_max=None,
                  iirf_h=100.0, t_mode="mid", outputs: Sequence[str] = ("C", "RF", "T"), stats: Optional[HistSpec] = None,
-                 precision="f64", return_state=True, chunk_members=16384, workspace=None, out=None,
+                 precision="f64", return_state=True, chunk_members=None, workspace=None, out=None,
                  gas_form="auto", conc_driven=None) -> EnsembleResult:
     """Integrate the 5-equation model for an ensemble (oxfair, .coveragerc:19, as one kernel launch).
 
@@ -237,6 +264,8 @@ def run_ensemble(emissions, gas_params, thermal_params, *, dt=1.0, scen_idx=None
     numpy / CPU tensors -> chunked host pipeline, results are numpy arrays.  For repeated host
     calls pass ``workspace=Workspace(...)`` (device staging reuse) and ``out=previous_result``
     (host output reuse; allocate those with :func:`pinned_result` for full-speed D2H).
+    ``chunk_members`` (host pipeline without a workspace): None picks 16 384 for link-bound calls and
+    131 072 for kernel-bound ones (:func:`auto_chunk_members`).
     """
     torch = _require_cuda()
     if precision not in ("f64", "f32"):
@@ -543,6 +572,10 @@ def _run_host(torch, E, gp, tp, dt, scen_idx, e_scale, f_ext, fext_per_member, s
         hist_p = host_out("hist", (n_t, stats.bins), np.int64)
         mom_p = host_out("moments", (n_t, _abi.MOM_COUNT), np.float64)
     own = workspace is None
+    if own and chunk_members is None:
+        chunk_members = auto_chunk_members(G, n_t, e_member=not e_scen, fext_member=fext_mode == _abi.FEXT_MEMBER, outputs=outputs,
+                                           return_state=return_state, state_in=state_in is not None,
+                                           e_scale=e_scale is not None, precision=precision)
     ws = Workspace(torch.cuda.current_device(), chunk_members) if own else workspace
     try:
         run = L.ufair_run_host_f64 if precision == "f64" else L.ufair_run_host_f32

@@ -106,10 +106,16 @@ static int run_chunks(ufair_workspace* ws, const ufair_desc* h, const ufair_desc
   const int64_t chunk = std::min<int64_t>(ws->chunk, std::max<int64_t>(fit, 256));
   const size_t hp = (size_t)ldh * es, dp = (size_t)chunk * es;  // host / device row pitch (bytes)
 
-  const int64_t n_chunk = (M + chunk - 1) / chunk;
-  for (int64_t c = 0; c < n_chunk; ++c) {
+  // Chunk schedule: the pipeline's fill time is the first chunk's copy-in (plus, when everything comes back, its
+  // kernel), during which nothing else runs -- so the first chunks are short and double up to the workspace's
+  // size (chunk/8, chunk/4, chunk/2, chunk, chunk, ...; never below 4096 members, whole 256-member groups).
+  // A kernel-bound call (few bytes per member: scenario inputs, statistics out) wants large chunks, which fill
+  // the GPU for several waves; with the ramp it no longer pays a large chunk's copy-in up front.
+  int64_t next = std::min<int64_t>(chunk, std::max<int64_t>(4096, (chunk / 8 + 255) / 256 * 256));
+  int64_t c0 = 0;
+  for (int64_t c = 0; c0 < M; ++c) {
     Stage& S = ws->st[c & 1];
-    const int64_t c0 = c * chunk, cm = std::min(chunk, M - c0);
+    const int64_t cm = std::min(next, M - c0);
     const size_t w = (size_t)cm * es;
     auto hsrc = [&](const void* base) { return (const void*)((const char*)base + (size_t)c0 * es); };
     auto hdst = [&](void* base) { return (void*)((char*)base + (size_t)c0 * es); };
@@ -198,6 +204,8 @@ static int run_chunks(ufair_workspace* ws, const ufair_desc* h, const ufair_desc
     if (rc != UFAIR_OK) return rc;
     CK(cudaEventRecord(S.out_done, ws->s_out), "cudaEventRecord");
     S.used = true;
+    c0 += cm;
+    next = std::min<int64_t>(chunk, next * 2);
   }
   return UFAIR_OK;
 }

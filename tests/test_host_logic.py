@@ -268,3 +268,23 @@ def test_shape_validation_of_scenario_inputs():
         _shapes((G, n_t, 5), (G, 17, M), (4, M), None, None, False)              # 5 columns, 64 members, no index
     assert _shapes((G, n_t, 1), (G, 17, M), (4, M), None, None, False)[3] is True   # one shared column is fine
     assert _shapes((G, n_t, M), (G, 17, M), (4, M), None, None, False)[3] is False
+
+
+def test_any_nonzero_and_auto_chunk_choice():
+    """The host-side form scan answers dense rows from their first element and all-zero rows in one pass, with the
+    answers of the plain comparison; the host pipeline's own chunk choice is small for link-bound calls and large for
+    kernel-bound ones."""
+    from fiveeqscm_b200 import concentrations as api
+    rng = np.random.default_rng(3)
+    for row in (np.zeros(1000), np.ones(1000), np.r_[np.zeros(999), 1e-300], np.r_[0.0, rng.standard_normal(5)], np.zeros(0),
+                np.array([-0.0, 0.0]), np.array([np.nan])):
+        assert api._any_nonzero(row) == bool(np.any(row != 0))
+    full = api.auto_chunk_members(3, 736, e_member=True, fext_member=False, outputs=("C", "RF", "T"))
+    stats_only = api.auto_chunk_members(3, 736, e_member=True, fext_member=False, outputs=(), return_state=False)
+    t_only = api.auto_chunk_members(3, 736, e_member=False, fext_member=False, outputs=("T",), return_state=False, e_scale=True)
+    scenario = api.auto_chunk_members(3, 736, e_member=False, fext_member=False, outputs=(), return_state=False, e_scale=True)
+    scenario32 = api.auto_chunk_members(3, 736, e_member=False, fext_member=False, outputs=(), return_state=False, e_scale=True,
+                                        precision="f32")
+    assert (full, stats_only, t_only) == (16384, 16384, 16384) and scenario == 131072 and scenario32 == 131072
+    short = api.auto_chunk_members(3, 10, e_member=False, fext_member=False, outputs=(), return_state=False)
+    assert short == 16384     # ten steps: the parameters going up outweigh the integration
