@@ -3,14 +3,16 @@
 // Work decomposition.  A WARP owns MW consecutive ensemble members and runs its own TMA pipeline
 // (its own shared-memory ring and mbarriers); warps never wait for each other -- there is NO
 // block-level synchronisation anywhere in the kernel.  Inside the warp a lane integrates either
-//   GPL = 1    : ONE gas of one member    (default; MW = 32, 16, 10, 8 members per warp for 1..4
-//                                          gases; the NGAS lanes of a member add up their forcings
-//                                          with warp shuffles), or
-//   GPL = NGAS : ALL gases of one member  (MW = 32; the FP32 default; -DUFAIR_GPL_ALL_F64=1 for FP64).
+//   GPL = NGAS : ALL gases of one member  (MW = 32: no idle lanes, no shuffles, one thermal step per member; the
+//                                          default for FP32, for the specialised forms, and since round 2 for FP64
+//                                          ensembles above UFAIR_SMALL_ENSEMBLE members), or
+//   GPL = 1    : ONE gas of one member    (MW = 32, 16, 10, 8 members per warp for 1..4 gases; the NGAS lanes of
+//                                          a member add up their forcings with warp shuffles; 3.2x as many warps,
+//                                          which is what small FP64 ensembles in the default alpha mode need).
 //   Pools, cumulative emissions and the two thermal boxes stay in REGISTERS across the serial time
-//   loop; most derived per-member constants sit in shared memory ([param][lane], conflict-free
-//   LDS.64 at base + immediate) so the registers they would pin are free for instruction-level
-//   parallelism across the independent pool / gas exponentials.
+//   loop.  The derived per-member constants sit in registers too where the register budget allows (all of
+//   them in the FP64 all-gases-per-lane kernels: 226-230 registers, 8 warps per SM; see UFAIR_REGCONST*), and
+//   otherwise in shared memory ([param][lane], conflict-free LDS.64 at base + immediate).
 //   Why: the loop is chains of dependent DFMAs (Horner polynomials); it is bound by the warp
 //   schedulers' issue rate and dependent-issue latency, not by HBM.  ncu history (profiles/):
 //     v1 thread per member, everything in regs (255), 2 warps/SMSP: FP64 pipe 35 %, IPC 0.37
@@ -31,8 +33,13 @@
 //        TT = 8; histogram moved out of the loop into the statistics pass (36.4 -> 33.7 ms); the plain
 //        instantiation without run-time switches (-> 32.9); the 17 hottest per-lane constants in
 //        registers at 16 warps/SM (-> 31.8 ms alone, 32-33.5 ms sustained): 221 instr per warp-step,
-//        143 of them FP64, FP64 pipe 72 %.  Every variant fits cycles ~ 2 N_FP64 + N_other per
-//        warp-step.
+//        143 of them FP64, FP64 pipe 72 %.
+//     round 2: the "2 N_FP64 + N_other" cost model of round 1 was wrong (tools/micro/: the pipes issue
+//        independently; a DFMA reading three different registers holds the FP64 pipe 3 cycles, everything else 2;
+//        dependent-issue latency 8 cycles).  Branch-free logarithm (its special-case branch had put every gas in
+//        a basic block of its own), all gases per lane again (33.1 -> 29.6 ms), every per-lane constant in
+//        registers at 8 warps/SM (-> 27.0), 8-step tiles (-> 26.0-27.2 ms, 0.69-0.72 of the FP64 roofline):
+//        569 instr per 32-member warp-step, 407 of them FP64, FP64 pipe 80 % (profiles/r2_final_summary.md).
 //   The loop body is alpha_val -> step_conc -> step_forc -> step_temp, the names the reference
 //   reserves in .coveragerc:12-19; `oxfair` is ONE launch.
 //
