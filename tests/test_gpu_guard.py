@@ -10,6 +10,9 @@ while every word inside has been written.  Inputs get the same treatment: a read
 would pull in the NaN poison and show up in the comparison with the oracle.
 """
 import ctypes as C
+import os
+import subprocess
+import sys
 
 import numpy as np
 import pytest
@@ -209,7 +212,7 @@ def test_host_pipeline_with_a_chunk_that_does_not_divide_M(prec):
 
 
 # ------------------------------------------------------------------ the checked build (libufair_dbg.so)
-_DBG = __import__("os").path.join(__import__("os").path.dirname(_abi.lib_path()), "libufair_dbg.so")
+_DBG = os.path.join(os.path.dirname(_abi.lib_path()), "libufair_dbg.so")
 _TRIP = """
 import numpy as np, torch
 from fiveeqscm_b200 import concentrations as api
@@ -221,7 +224,7 @@ print("completed")
 """
 
 
-@pytest.mark.skipif(not __import__("os").path.exists(_DBG), reason="libufair_dbg.so not built (make -C fiveeqscm_b200/csrc debug)")
+@pytest.mark.skipif(not os.path.exists(_DBG), reason="libufair_dbg.so not built (make -C fiveeqscm_b200/csrc debug)")
 def test_debug_bounds_build_never_traps_and_its_checks_are_live():
     """The same library compiled with -DUFAIR_DEBUG_BOUNDS traps on any output store outside its array
     (or in a column >= n_member) and on any read of the shared-memory emission / forcing rings outside
@@ -229,9 +232,6 @@ def test_debug_bounds_build_never_traps_and_its_checks_are_live():
     subprocess (a trap poisons the CUDA context) and must pass; then the negative control: with
     UFAIR_DEBUG_TRIP=1 the store check pretends the last row of every array is missing, and the very
     same run must die with a launch failure -- so the checks are really compiled in and reached."""
-    import os
-    import subprocess
-    import sys
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     env = dict(os.environ, UFAIR_LIB=_DBG, PYTHONPATH=root)
     env.pop("UFAIR_DEBUG_TRIP", None)
