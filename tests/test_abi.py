@@ -64,6 +64,8 @@ def test_argument_errors_are_reported_not_fatal(built):
     assert L.ufair_run_f64(ctypes.byref(d), None) == _abi.ERR_ARG
     d = _abi.UfairDesc(n_gas=1, n_t=4, n_member=4, ld_member=4, alpha_mode=7)
     assert L.ufair_run_f64(ctypes.byref(d), None) == _abi.ERR_ARG
+    d = _abi.UfairDesc(n_gas=1, n_t=4, n_member=4, ld_member=2 ** 31)   # TMA coordinates are 32-bit
+    assert L.ufair_run_f64(ctypes.byref(d), None) == _abi.ERR_ARG and b"split the member axis" in L.ufair_last_error()
     with pytest.raises(_abi.UfairError):
         _abi.check(L.ufair_run_f32(ctypes.byref(d), None))
 
