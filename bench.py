@@ -712,7 +712,13 @@ def main():
         solo_up, solo_down = probe(unit, 0, reps), probe(0, unit, reps)
         L.ufair_link_probe(local, 0, 0, 0, 1, g2, None)
         t_mix = float(mix[:, 2].max())                         # the slowest rank sets the step, as in e2e
-        ceiling_value = float(Me) * n_t * n_gpus / (t_mix * (d2h / (down_b // rows * rows * float(reps))))
+        mix_value = float(Me) * n_t * n_gpus / (t_mix * (d2h / (down_b // rows * rows * float(reps))))
+        # the ceiling proper: no pipeline can beat the busier direction moving its bytes at the rate that direction
+        # reaches ALONE with every rank copying (aggregate over ranks: all of them have to finish)
+        per_probe = float(unit // rows * rows) * reps
+        agg_up = world * per_probe / float(solo_up[:, 2].max())
+        agg_down = world * per_probe / float(solo_down[:, 2].max())
+        ceiling_value = float(Me) * n_t * n_gpus / max(world * d2h / agg_down, world * h2d / agg_up)
 
         barrier()
         t0 = time.perf_counter()
@@ -741,14 +747,17 @@ def main():
                 "h2d_alone": triple(solo_up[:, 0]), "d2h_alone": triple(solo_down[:, 1]),
                 "h2d_in_pipeline_mix": triple(mix[:, 0]), "d2h_in_pipeline_mix": triple(mix[:, 1])},
             "ceiling_value": ceiling_value, "frac_of_ceiling": e2e_value / ceiling_value,
+            "mix_estimate_value": mix_value, "frac_of_mix_estimate": e2e_value / mix_value,
             "achieved_gbs_per_rank": {"d2h_min": d2h * args.e2e_steps / float(times.max()) / 1e9,
                                       "d2h_max": d2h * args.e2e_steps / float(times.min()) / 1e9,
                                       "h2d_min": h2d * args.e2e_steps / float(times.max()) / 1e9,
                                       "h2d_max": h2d * args.e2e_steps / float(times.min()) / 1e9},
             "what": "run_ensemble(host pinned E/params -> all of C, RF, T, state + histogram back on the host), "
                     "chunked %d members, H2D/kernel/D2H overlapped on 3 streams; wall clock, max over ranks; "
-                    "ceiling_value = the same bytes at the link rates measured just before with all ranks copying "
-                    "(both directions at once in the pipeline's %.2f : 1 down : up ratio)" % (args.e2e_chunk, d2h / h2d)}
+                    "ceiling_value = the busier direction's bytes at the aggregate rate that direction reaches alone with all "
+                    "ranks copying, measured just before (an upper bound: no interference between the directions); "
+                    "mix_estimate_value = the same bytes at the rates of a probe that drives both directions flat out at once in "
+                    "the pipeline's %.2f : 1 down : up ratio (pessimistic: the pipeline's copy-in is spread out)" % (args.e2e_chunk, d2h / h2d)}
         # secondary: the configs[3] use case proper -- host inputs in, only the ensemble statistics back
         # (histogram + moments; no trajectory leaves the GPU), same chunked pipeline
         if spec is not None:
