@@ -707,7 +707,9 @@ def main():
             return v.cpu().numpy()
         unit = 192 << 20
         up_b, down_b = int(unit * h2d / d2h), unit
-        reps = 4
+        # long enough that the ranks' start skew after the barrier (milliseconds) does not let the early ones see an idle
+        # link: 0.8 GB per direction at N = 1 (15 ms), 6 GB at N = 8 (0.4 s at the ~15 GB/s a rank gets there)
+        reps = 4 * world
         mix = probe(up_b, down_b, reps)
         solo_up, solo_down = probe(unit, 0, reps), probe(0, unit, reps)
         L.ufair_link_probe(local, 0, 0, 0, 1, g2, None)
