@@ -620,6 +620,18 @@ def main():
                     "peak_burst": peaks[bound + "_tflops_burst"], "frac_of_burst": a_fp / peaks[bound + "_tflops_burst"],
                     "peak_source": peaks["fma_source"]},
         })
+        # The FMA peak is measured by a pure DFMA / FFMA loop, which draws less power than the integrator and therefore
+        # runs at a higher clock under the board's power cap.  `frac` stays against that measured peak; this entry only
+        # says how much of the gap is the clock (informational).
+        try:
+            per_sm = 128.0 if bound == "fp64" else 256.0      # FMA flops per cycle and SM: 64 FP64 / 128 FP32 lanes
+            implied = fpeak * 1e12 / (torch.cuda.get_device_properties(local).multi_processor_count * per_sm) / 1e6
+            if clk and clk.get("sm_mhz"):
+                roof["clock_note"] = {"peak_measured_at_mhz": implied, "kernel_ran_at_mhz": clk["sm_mhz"],
+                                      "frac_of_pipe_at_kernel_clock": (a_fp / fpeak) * implied / float(clk["sm_mhz"]),
+                                      "what": "the pipe peak scaled to the SM clock sampled during the timed region (median, nvidia-smi)"}
+        except Exception:
+            pass
         line["roofline"] = roof
     del plan, res, reducer
     torch.cuda.empty_cache()
